@@ -1,0 +1,41 @@
+import json
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+SCENES = ["cornell", "mesh", "single-sphere", "two-spheres", "three-spheres", "cartesian"]
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def scene_path(scene_id: str) -> str:
+    return os.path.join(ROOT, "scenes", f"{scene_id}.json")
+
+
+CAMERA = {"position": [0.0, 0.0, 0.0], "direction": [0.0, 0.0, -1.0], "focal_length": 0.035,
+          "sensor_width": 0.036, "aspect_ratio": 1.5}
+
+
+def sphere_obj(pos, radius=1.0, color=(1.0, 0.0, 0.0), emission=(0.0, 0.0, 0.0), refl="Diffuse"):
+    return {"type_": {"Sphere": {"radius": radius}}, "position": list(pos),
+            "material": {"color": list(color), "emmission": list(emission), "reflect_type": refl}}
+
+
+def write_scene(path, objects, scene_id="kat", camera=None):
+    with open(path, "w") as f:
+        json.dump({"id": scene_id, "objects": objects, "camera": camera or CAMERA}, f)
+    return str(path)
+
+
+@pytest.fixture
+def kat_scene(tmp_path):
+    def make(objects, name="kat", camera=None):
+        return write_scene(tmp_path / f"{name}.json", objects, name, camera)
+    return make

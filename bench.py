@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 path-tracing backend (see BASELINE.json / SURVEY.md 8d).
+
+Metric: Mpaths/s (pixel-samples per second) on scenes/cornell.json at 3840x2160 x 4096 spp, the samples sharded across
+the N GPUs of one box (strong scaling: total work fixed) and summed with one NCCL reduce; Mray-segments/s is reported
+beside it.  A "step" is one full frame (all 4096 spp of every pixel).  `value` is timed with the scene resident on the
+device; `e2e` goes through the public host API with the scene uploaded from host memory and the image read back to
+pinned host memory inside the timed region.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--spp S]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+`--impl reference` times the CPU path (the strict-fp32 C restatement in oracle/; the Rust reference cannot be built in this
+image) on a bounded sample of the same workload, on rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOADS = {
+    # name: (scene id, W, H, spp)   -- BASELINE.json configs
+    "cornell4k": ("cornell", 3840, 2160, 4096),      # configs[3], the multi-GPU headline
+    "cornell_default": ("cornell", 450, 300, 100),   # configs[0]
+    "single_sphere_1080p": ("single-sphere", 1920, 1080, 256),
+    "three_spheres_1080p": ("three-spheres", 1920, 1080, 256),
+    "mesh_1080p": ("mesh", 1920, 1080, 1024),        # configs[2]
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d.get("hbm_gbs", 6650.0), "sm_max_mhz": d.get("sm_max_mhz", 1965.0), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """Samples SM clocks and throttle reasons of one GPU during the timed region (NVML, else nvidia-smi)."""
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._th = None
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nvml = None
+
+    def _loop(self):
+        nv = self._nvml
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+                 0x80: "hw_power_brake_slowdown"}
+        while not self._stop.wait(0.2):
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                break
+
+    def start(self):
+        if self._nvml is not None:
+            self._th = threading.Thread(target=self._loop, daemon=True)
+            self._th.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._th:
+            self._th.join()
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_reference_run(scene_id: str, W: int, H: int, target_s: float, threads: int | None = None):
+    """Times the CPU path (oracle in the reference's own mode: sequential RNG, libm sin/cos, recursive radiance,
+    shuffled pixels, all host threads) on a bounded sample: the same scene and camera at 1/16 of the resolution per axis,
+    spp chosen by a short calibration so the run takes about `target_s` seconds."""
+    import oracle_lib as O
+    threads = threads or os.cpu_count() or 1
+    osc = O.OracleScene(os.path.join(ROOT, "scenes", f"{scene_id}.json"))
+    w, h = max(W // 16, 16), max(H // 16, 16)
+    ref = dict(rng=O.RNG_SEQ, sincos=O.SINCOS_LIBM, accum=O.ACCUM_RECURSIVE, threads=threads, shuffle=1)
+    t0 = time.perf_counter()
+    osc.render_sum(w, h, 4, seed=1, **ref)
+    cal = max(time.perf_counter() - t0, 1e-4)
+    spp = int(max(4, min(4096, 4 * target_s / cal)))
+    t0 = time.perf_counter()
+    _, st = osc.render_sum(w, h, spp, seed=2, **ref)
+    dt = time.perf_counter() - t0
+    samples = w * h * spp
+    return {"seconds": dt, "samples": samples, "segments": int(st[0]), "mpaths_s": samples / dt * 1e-6,
+            "mseg_s": int(st[0]) / dt * 1e-6, "threads": threads,
+            "tests_per_segment": {"sphere": int(st[1]) / max(int(st[0]), 1), "gate": int(st[2]) / max(int(st[0]), 1),
+                                  "triangle": int(st[3]) / max(int(st[0]), 1)},
+            "sample": f"{scene_id}.json same camera at {w}x{h} (1/256 of the {W}x{H} pixels) x {spp} spp, "
+                      f"{threads} threads, pixel loop only"}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    scene_id, W, H, spp = WORKLOADS[args.workload]
+    if args.spp:
+        spp = args.spp
+    per_step = max(2.0, min(20.0, 150.0 / max(args.steps + args.warmup, 1)))
+    for _ in range(args.warmup):
+        cpu_reference_run(scene_id, W, H, per_step)
+    runs = [cpu_reference_run(scene_id, W, H, per_step) for _ in range(args.steps)]
+    tot_t = sum(r["seconds"] for r in runs)
+    val = sum(r["samples"] for r in runs) / tot_t * 1e-6
+    seg = sum(r["segments"] for r in runs) / tot_t * 1e-6
+    line = {"impl": "reference", "metric": "Mpaths/s", "value": val, "unit": "Mpaths/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": tot_t / max(args.steps, 1) * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: scenes/{scene_id}.json {W}x{H} x {spp} spp", "scene": scene_id, "width": W,
+                       "height": H, "spp": spp},
+            "mray_segments_per_s": seg,
+            "cpu_baseline": {"value": val, "unit": "Mpaths/s", "cores": runs[-1]["threads"], "kind": "port", "sample": runs[-1]["sample"]},
+            "e2e": {"value": val, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cornell4k", choices=sorted(WORKLOADS))
+    ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (development only; recorded in config)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import path_tracer_rust_b200 as P
+    from path_tracer_rust_b200.distributed import CudaShardRenderer, render_sharded, shard_samples
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the backend has no CPU fallback (use --impl reference for the CPU path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    else:
+        dist = None
+
+    scene_id, W, H, spp = WORKLOADS[args.workload]
+    reduced = bool(args.spp)
+    if args.spp:
+        spp = args.spp
+    scene = P.Scene.load(scene_id)
+    be = P.Backend(local_rank)
+    be.upload_scene(scene)
+    shard = CudaShardRenderer(be, W, H, seed=2026, device=dev)
+    nfl = W * H * 3
+    host_img = torch.empty(nfl, dtype=torch.float32).pin_memory() if rank == 0 else None
+    l2_flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        return render_sharded(shard, spp, rank, world)
+
+    def step_e2e():
+        be.upload_scene(scene)                       # H2D of the scene (flatten + upload + device BVH build)
+        img = render_sharded(shard, spp, rank, world)
+        if rank == 0:
+            host_img.copy_(img, non_blocking=True)   # D2H of the resolved image
+            torch.cuda.current_stream().synchronize()
+            return float(host_img[0])
+        return None
+
+    # ---- warm-up -------------------------------------------------------------------------------------------------
+    for _ in range(max(args.warmup, 0)):
+        step_resident()
+    barrier()
+
+    # ---- timed: K steps, CUDA events on the launching stream, L2 flushed between steps ------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    seg_total, launches = 0, 0
+    times = []
+    for _ in range(args.steps):
+        l2_flush.fill_(1.0)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step_resident()
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+        st = be.stats()
+        seg_total += st["segments"]
+        launches += st["kernel_launches"] + (1 if rank == 0 else 0)
+    barrier()
+    clocks = sampler.stop()
+    kernel_ms_last = be.stats()["render_ms"]
+
+    # ---- e2e through the host API ------------------------------------------------------------------------------------
+    e2e_times = []
+    step_e2e()
+    for _ in range(args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        step_e2e()
+        torch.cuda.synchronize()
+        e2e_times.append((time.perf_counter() - t0) * 1e3)
+    barrier()
+
+    t_sum = torch.tensor([sum(times), sum(e2e_times), float(seg_total), float(launches)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        t_max = t_sum.clone()
+        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t_sum, op=dist.ReduceOp.SUM)
+        total_ms, e2e_ms = float(t_max[0]), float(t_max[1])
+        seg_total, launches = float(t_sum[2]), int(t_sum[3])
+    else:
+        total_ms, e2e_ms = float(t_sum[0]), float(t_sum[1])
+
+    if rank == 0:
+        peaks = load_peaks()
+        samples_per_step = W * H * spp
+        value = samples_per_step * args.steps / (total_ms * 1e-3) * 1e-6
+        seg_rate = seg_total / (total_ms * 1e-3) * 1e-6
+        e2e_value = samples_per_step * args.steps / (e2e_ms * 1e-3) * 1e-6
+        sd = scene._desc.contents
+        scene_bytes = int(sd.n_objects) * 80 + int(sd.n_triangles) * 36 + 36
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            cpu = cpu_reference_run(scene_id, W, H, 12.0)
+        # roofline of the dominant kernel (k_render): FP32 issue slots.  Algorithmic flops per segment follow SURVEY.md 8d:
+        # 17 per sphere/gate test + 45 per triangle test + 120 shading, with the reference algorithm's own test counts.
+        tps = cpu["tests_per_segment"] if cpu else None
+        if tps is None:
+            tps = {"sphere": 4.0, "gate": 7.0, "triangle": 11.0} if scene_id == "cornell" else {"sphere": 0, "gate": 0, "triangle": 0}
+        flops_per_seg = 17.0 * (tps["sphere"] + tps["gate"]) + 45.0 * tps["triangle"] + 120.0
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        fp32_peak = sms * 128 * peaks["sm_max_mhz"] * 1e6 * 1e-12          # T lane-ops/s, un-fused (FMA is barred by parity)
+        seg_per_gpu = seg_total / max(world, 1) / args.steps
+        kern_s = kernel_ms_last * 1e-3
+        achieved = seg_per_gpu * flops_per_seg / kern_s * 1e-12 if kern_s > 0 else None
+        line = {
+            "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / max(args.steps, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: scenes/{scene_id}.json {W}x{H} x {spp} spp, spp sharded over {world} GPU(s), "
+                                   "NCCL fp32 sum-reduce", "scene": scene_id, "width": W, "height": H, "spp": spp,
+                       "spp_reduced_for_development": reduced, "l2": "flushed between steps (256 MiB device write)",
+                       "parallelism": f"spp-shard x{world}"},
+            "mray_segments_per_s": seg_rate, "segments_per_sample": seg_total / (samples_per_step * args.steps),
+            "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": scene_bytes, "d2h_bytes_per_step": nfl * 4,
+                    "ms_per_step": e2e_ms / max(args.steps, 1)},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "fp32_issue", "achieved": achieved, "peak": fp32_peak, "unit": "Tlane-op/s",
+                         "frac": (achieved / fp32_peak) if achieved else None, "traffic": None,
+                         "kernel": "k_render", "flops_per_segment": flops_per_seg, "kernel_ms": kernel_ms_last,
+                         "peak_source": f"SMs({sms}) x 128 lanes x sm_max_mhz({peaks['sm_max_mhz']}) from MEASURED_PEAKS.json ({peaks['source']}); "
+                                        "no tensor or HBM bound applies: scene and path state live in shared memory / registers"},
+            "cpu_baseline": ({"value": cpu["mpaths_s"], "unit": "Mpaths/s", "cores": cpu["threads"], "kind": "port",
+                              "sample": cpu["sample"], "mray_segments_per_s": cpu["mseg_s"]} if cpu else None),
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    be.close()
+
+
+if __name__ == "__main__":
+    main()

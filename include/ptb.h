@@ -1,0 +1,143 @@
+/*
+ * ptb.h -- C ABI of the B200 path-tracing backend (libptb.so).
+ *
+ * Drop-in boundary for the reference's rayon render path.  The reference has no FFI today; the
+ * narrowest seam is `pub fn render(RenderConfig, &mut Sink<RenderUpdate>, Arc<AtomicBool>) -> RenderDone`
+ * (src/render/mod.rs:928-934, sole caller src/main.rs:364).  A Rust maintainer keeps that
+ * signature and replaces the body of the pixel loop (mod.rs:998-1024) by the calls declared here;
+ * INTEGRATION.md shows the `extern "C"` block and build.rs step.  Every entry point below names the
+ * reference interface it replaces (paths relative to the reference root).
+ *
+ * Conventions: plain C types only; return 0 = PTB_OK, <0 = error (message via ptb_last_error),
+ * PTB_CANCELLED (1) = stopped early by the cancel flag.  Nothing throws or aborts across the
+ * boundary.  The caller owns every host buffer it passes; the library owns all device memory
+ * behind the opaque ptb_ctx.  One ctx = one CUDA device, used from one host thread at a time
+ * (multi-GPU = one process / one ctx per GPU, framebuffers summed by the caller's collective).
+ * There is NO CPU fallback: every compute entry point fails with PTB_ERR_CUDA without a device.
+ */
+#ifndef PTB_H
+#define PTB_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PTB_OK 0
+#define PTB_CANCELLED 1
+#define PTB_ERR_ARG (-1)
+#define PTB_ERR_CUDA (-2)
+#define PTB_ERR_IO (-3)
+#define PTB_ERR_PARSE (-4)
+#define PTB_ERR_STATE (-5)
+#define PTB_ERR_LIMIT (-6)
+
+#define PTB_ABI_VERSION 1
+
+typedef struct ptb_ctx ptb_ctx;     /* device context: streams, scene buffers, BVH, framebuffer */
+typedef struct ptb_scene ptb_scene; /* host-side scene loaded from scenes/<id>.json (+ OFF meshes) */
+
+/* ---- data model: mirrors SceneData / SceneObjectData / Material / CameraData ------------------- */
+
+enum { PTB_OBJ_SPHERE = 0, PTB_OBJ_MESH = 1 };                         /* SceneObject,  mod.rs:327-335 */
+enum { PTB_REFL_DIFFUSE = 0, PTB_REFL_SPECULAR = 1, PTB_REFL_REFRACT = 2 }; /* ReflectType, mod.rs:72-76 */
+
+typedef struct ptb_triangle { /* Triangle{a,b,c}, mod.rs:539-543 (mesh-local, before the +position translate) */
+    float a[3], b[3], c[3];
+} ptb_triangle;
+
+typedef struct ptb_object { /* SceneObjectData{type_, position, material}, mod.rs:254-258 + Material mod.rs:79-83 */
+    int32_t kind;           /* PTB_OBJ_* */
+    int32_t reflect_type;   /* PTB_REFL_* */
+    float position[3];
+    float color[3];
+    float emission[3];      /* `emmission` (sic) */
+    float radius;           /* Sphere{radius} */
+    float bs_position[3];   /* Mesh.bounding_sphere.position (mesh-local; mod.rs:446) */
+    float bs_radius;        /* Mesh.bounding_sphere.radius */
+    uint64_t tri_begin;     /* Mesh.triangles = triangles[tri_begin .. tri_begin+tri_count) */
+    uint64_t tri_count;
+} ptb_object;
+
+typedef struct ptb_camera { /* CameraData, mod.rs:163-176; `direction` is used as stored (not renormalised) */
+    float position[3];
+    float direction[3];
+    float focal_length, sensor_width, aspect_ratio;
+} ptb_camera;
+
+typedef struct ptb_scene_desc { /* SceneData{objects, camera}, mod.rs:121-125 */
+    const ptb_object *objects;
+    uint64_t n_objects;
+    const ptb_triangle *triangles;
+    uint64_t n_triangles;
+    ptb_camera camera;
+} ptb_scene_desc;
+
+typedef struct ptb_stats {
+    uint64_t segments;        /* closest-hit queries (intersect_scene calls, mod.rs:663) of the last render */
+    uint64_t samples;         /* pixel-samples of the last render */
+    double render_ms;         /* device time of the render kernels of the last render (CUDA events) */
+    double upload_ms;         /* last ptb_upload_scene: H2D + flatten */
+    double bvh_build_ms;      /* last ptb_upload_scene: device BVH build */
+    uint32_t kernel_launches; /* kernels launched by the last render / query call */
+    uint32_t n_loose_objects, n_loose_triangles;   /* brute-force (shared-memory) part of the scene */
+    uint32_t n_bvh_triangles, n_bvh_spheres, n_bvh_nodes;
+} ptb_stats;
+
+/* ---- host-side scene I/O: SceneDescriptor::load + to_data (mod.rs:92-110, 304-318), load_off.rs:8-85 ---- */
+int ptb_scene_load_json(const char *json_path, const char *base_dir, ptb_scene **out, char *err, size_t errlen);
+const ptb_scene_desc *ptb_scene_get_desc(const ptb_scene *scene);
+const char *ptb_scene_id(const ptb_scene *scene);
+void ptb_scene_free(ptb_scene *scene);
+
+/* ---- context ---------------------------------------------------------------------------------- */
+int ptb_abi_version(void);
+int ptb_device_count(void);
+int ptb_create(int device_id, ptb_ctx **out);
+void ptb_destroy(ptb_ctx *ctx);
+const char *ptb_last_error(const ptb_ctx *ctx); /* ctx may be NULL: last error of the calling thread */
+
+/* Replaces the `&config.scene.objects` borrow of render_pixel (mod.rs:802): flattens to SoA (pre-translated
+ * triangles A'=a+pos, E1, E2 with the reference's own roundings), uploads, builds the device BVH. */
+int ptb_upload_scene(ptb_ctx *ctx, const ptb_scene_desc *desc);
+int ptb_get_stats(const ptb_ctx *ctx, ptb_stats *out);
+
+/* ---- the hot path: replaces the rayon loop + render_pixel + radiance (mod.rs:1001-1024, 794-857, 662-792) --
+ * Renders global sample indices [spp_begin, spp_begin+spp_count) of every pixel.  `out_rgb` is W*H*3 fp32 in the
+ * reference's buffer order (index i <-> x = i % W, y = H-1 - i / W, mod.rs:805-806):
+ *   PTB_OUT_MEAN : sum / spp_count clamped to [0,1]  == Image.pixels (mod.rs:849-856)
+ *   PTB_OUT_SUM  : raw fp32 radiance sum (for spp-sharded multi-GPU / progressive use; add, then resolve)
+ * `cancel` (may be NULL) is polled between launches like stop_render (mod.rs:1003); `samples_done` (may be NULL)
+ * receives pixel-samples finished so far (processed_pixel_count analogue, mod.rs:850). */
+enum { PTB_OUT_MEAN = 0, PTB_OUT_SUM = 1 };
+int ptb_render(ptb_ctx *ctx, int width, int height, uint64_t spp_begin, uint64_t spp_count, uint64_t seed,
+               int out_kind, float *out_rgb, const volatile int32_t *cancel, volatile uint64_t *samples_done);
+
+/* Same, accumulating into a caller-provided DEVICE sum framebuffer (W*H*3 fp32, += in sample order) on
+ * `cuda_stream` (a cudaStream_t; NULL = the default stream).  Asynchronous unless cancel/samples_done is given. */
+int ptb_render_device(ptb_ctx *ctx, int width, int height, uint64_t spp_begin, uint64_t spp_count, uint64_t seed,
+                      float *d_sum_rgb, void *cuda_stream, const volatile int32_t *cancel,
+                      volatile uint64_t *samples_done);
+/* radiance / spp then clamp (mod.rs:849-856) on device buffers; d_mean may alias d_sum */
+int ptb_resolve_device(ptb_ctx *ctx, const float *d_sum_rgb, uint64_t n_floats, uint64_t spp_total, float *d_mean_rgb,
+                       void *cuda_stream);
+
+/* ---- parity hooks ----------------------------------------------------------------------------- */
+/* intersect_scene (mod.rs:631-659) for the deterministic centre ray of every pixel (xsub=ysub=xfilter=yfilter=0
+ * in mod.rs:833-838).  obj = object index or -1, tri = triangle index inside the mesh or -1, t = distance. */
+int ptb_primary_hits(ptb_ctx *ctx, int width, int height, int32_t *obj, int32_t *tri, float *t);
+/* intersect_scene for n arbitrary rays (origin xyz, direction xyz).  point/normal may be NULL. */
+int ptb_intersect(ptb_ctx *ctx, const float *rays6, uint64_t n, int32_t *obj, int32_t *tri, float *t, float *point3,
+                  float *normal3);
+
+/* ---- output resolve: mod.rs:57-63 (gamma), :1042-1076 (P3 PPM, reversed pixel order), :916-926 (hash) ---- */
+uint32_t ptb_to_int_with_gamma_correction(float x);
+int ptb_write_ppm(const char *path, const float *mean_rgb, int width, int height, uint64_t spp, const char *scene_id,
+                  uint64_t seconds);
+uint64_t ptb_hash_pixels(const float *rgb, uint64_t n_pixels);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTB_H */

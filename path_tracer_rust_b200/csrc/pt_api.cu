@@ -1,0 +1,490 @@
+// pt_api.cu -- the C ABI (include/ptb.h): context, scene flatten + upload, render driver, parity hooks.
+//
+// Replaces the render thread of render() (src/render/mod.rs:984-1026): instead of shuffling a pixel list into a
+// rayon pool it launches the persistent integrator kernel in sample batches, polling the cancel flag between
+// launches (mod.rs:1003) and publishing progress (mod.rs:850).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ptb.h"
+#include "pt_bvh_build.h"
+#include "pt_launch.h"
+#include "scene_io.hpp"
+
+using namespace ptb;
+
+namespace {
+
+thread_local std::string g_thread_error;
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    cudaError_t resize(size_t count) {
+        if (count <= n && p) return cudaSuccess;
+        release();
+        if (count == 0) return cudaSuccess;
+        cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&p), count * sizeof(T));
+        if (e == cudaSuccess) n = count; else p = nullptr;
+        return e;
+    }
+    cudaError_t upload(const std::vector<T> &h, cudaStream_t st) {
+        cudaError_t e = resize(std::max<size_t>(h.size(), 1));
+        if (e != cudaSuccess || h.empty()) return e;
+        return cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st);
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+    }
+};
+
+inline float4 f4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+inline float ibits(int32_t v) { float f; std::memcpy(&f, &v, 4); return f; }
+inline float ubits(uint32_t v) { float f; std::memcpy(&f, &v, 4); return f; }
+inline V3 v3(const float *p) { return mk3(p[0], p[1], p[2]); }
+
+}  // namespace
+
+struct ptb_scene {
+    HostScene host;
+};
+
+struct ptb_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    bool has_scene = false;
+    DScene ds{};
+    DevBuf<float4> loose_obj, loose_tri, obj_gate, mat_color, mat_emis;
+    BvhDevice bvh;
+    DevBuf<float> fb, scratch_f;
+    DevBuf<int> scratch_i;
+    DevBuf<int> tile_counter;
+    DevBuf<unsigned long long> seg_counter;
+    ptb_stats stats{};
+    size_t max_smem_optin = 0;
+    // an asynchronous ptb_render_device leaves its counters on the device until ptb_get_stats asks for them
+    mutable bool stats_pending = false;
+    mutable cudaStream_t pending_stream = nullptr;
+};
+
+namespace {
+
+int fail(ptb_ctx *ctx, int code, const std::string &msg) {
+    g_thread_error = msg;
+    if (ctx) ctx->err = msg;
+    return code;
+}
+int cuda_fail(ptb_ctx *ctx, cudaError_t e, const char *what) {
+    return fail(ctx, PTB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")");
+}
+#define CU(ctx, expr)                                             \
+    do {                                                          \
+        cudaError_t e__ = (expr);                                 \
+        if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #expr); \
+    } while (0)
+
+double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// host-side scene I/O
+// ------------------------------------------------------------------------------------------------
+extern "C" int ptb_scene_load_json(const char *json_path, const char *base_dir, ptb_scene **out, char *err, size_t errlen) {
+    if (err && errlen) err[0] = 0;
+    if (!json_path || !out) return fail(nullptr, PTB_ERR_ARG, "ptb_scene_load_json: null argument");
+    try {
+        auto *s = new ptb_scene;
+        s->host = load_scene_json(json_path, base_dir ? base_dir : "");
+        s->host.refresh_desc();
+        *out = s;
+        return PTB_OK;
+    } catch (const SceneError &e) {
+        if (err && errlen) std::snprintf(err, errlen, "%s", e.what());
+        return fail(nullptr, e.code, e.what());
+    } catch (const std::exception &e) {
+        if (err && errlen) std::snprintf(err, errlen, "%s", e.what());
+        return fail(nullptr, PTB_ERR_PARSE, e.what());
+    }
+}
+extern "C" const ptb_scene_desc *ptb_scene_get_desc(const ptb_scene *scene) { return scene ? &scene->host.desc : nullptr; }
+extern "C" const char *ptb_scene_id(const ptb_scene *scene) { return scene ? scene->host.id.c_str() : ""; }
+extern "C" void ptb_scene_free(ptb_scene *scene) { delete scene; }
+
+extern "C" uint32_t ptb_to_int_with_gamma_correction(float x) { return to_int_with_gamma_correction(x); }
+extern "C" int ptb_write_ppm(const char *path, const float *mean_rgb, int width, int height, uint64_t spp, const char *scene_id,
+                             uint64_t seconds) {
+    if (!path || !mean_rgb || width <= 0 || height <= 0) return fail(nullptr, PTB_ERR_ARG, "ptb_write_ppm: bad argument");
+    try {
+        write_ppm(path, mean_rgb, width, height, spp, scene_id ? scene_id : "", seconds);
+        return PTB_OK;
+    } catch (const SceneError &e) {
+        return fail(nullptr, e.code, e.what());
+    }
+}
+extern "C" uint64_t ptb_hash_pixels(const float *rgb, uint64_t n_pixels) { return rgb ? hash_pixels(rgb, n_pixels) : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+extern "C" int ptb_abi_version(void) { return PTB_ABI_VERSION; }
+
+extern "C" int ptb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" const char *ptb_last_error(const ptb_ctx *ctx) { return ctx ? ctx->err.c_str() : g_thread_error.c_str(); }
+
+extern "C" void ptb_destroy(ptb_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    ctx->loose_obj.release(); ctx->loose_tri.release(); ctx->obj_gate.release(); ctx->mat_color.release();
+    ctx->mat_emis.release(); ctx->fb.release(); ctx->scratch_f.release(); ctx->scratch_i.release();
+    ctx->tile_counter.release(); ctx->seg_counter.release();
+    bvh_release(ctx->bvh);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int ptb_create(int device_id, ptb_ctx **out) {
+    if (!out) return fail(nullptr, PTB_ERR_ARG, "ptb_create: out is null");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(nullptr, PTB_ERR_CUDA, "ptb_create: no CUDA device (this backend has no CPU fallback)");
+    }
+    if (device_id < 0 || device_id >= n) return fail(nullptr, PTB_ERR_ARG, "ptb_create: device_id out of range");
+    auto *ctx = new ptb_ctx;
+    ctx->device = device_id;
+    auto bail = [&](cudaError_t ce, const char *what) {
+        int rc = cuda_fail(nullptr, ce, what);
+        ptb_destroy(ctx);
+        return rc;
+    };
+    if ((e = cudaSetDevice(device_id)) != cudaSuccess) return bail(e, "cudaSetDevice");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device_id)) != cudaSuccess) return bail(e, "cudaGetDeviceProperties");
+    if (prop.major != 10) {
+        ptb_destroy(ctx);
+        return fail(nullptr, PTB_ERR_CUDA, std::string("ptb_create: built for sm_100a only, device is ") + prop.name);
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->max_smem_optin = prop.sharedMemPerBlockOptin;
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if ((e = ctx->tile_counter.resize(1)) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = ctx->seg_counter.resize(1)) != cudaSuccess) return bail(e, "cudaMalloc");
+    // parity self-test: the kernels must have been built with --fmad=false
+    if ((e = ctx->scratch_f.resize(4)) != cudaSuccess) return bail(e, "cudaMalloc");
+    const float a = 1.0f + 1.0f / 8192.0f, c = -(1.0f + 1.0f / 4096.0f);
+    if ((e = launch_contraction_probe(a, a, c, ctx->scratch_f.p, ctx->stream)) != cudaSuccess) return bail(e, "probe launch");
+    float probe = 1.0f;
+    if ((e = cudaMemcpyAsync(&probe, ctx->scratch_f.p, 4, cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess) return bail(e, "probe copy");
+    if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return bail(e, "probe sync");
+    if (probe != 0.0f) {
+        ptb_destroy(ctx);
+        return fail(nullptr, PTB_ERR_STATE, "ptb_create: kernels were built with FMA contraction; rebuild with --fmad=false");
+    }
+    *out = ctx;
+    return PTB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// scene flatten + upload
+// ------------------------------------------------------------------------------------------------
+extern "C" int ptb_upload_scene(ptb_ctx *ctx, const ptb_scene_desc *desc) {
+    if (!ctx || !desc) return fail(ctx, PTB_ERR_ARG, "ptb_upload_scene: null argument");
+    if (desc->n_objects && !desc->objects) return fail(ctx, PTB_ERR_ARG, "ptb_upload_scene: objects is null");
+    if (desc->n_objects > (1u << 28) || desc->n_triangles > (1u << 28))
+        return fail(ctx, PTB_ERR_LIMIT, "ptb_upload_scene: more than 2^28 objects or triangles");
+    CU(ctx, cudaSetDevice(ctx->device));
+    const double t0 = now_ms();
+    const size_t nobj = desc->n_objects;
+    for (size_t i = 0; i < nobj; ++i) {
+        const ptb_object &o = desc->objects[i];
+        if (o.kind != PTB_OBJ_SPHERE && o.kind != PTB_OBJ_MESH) return fail(ctx, PTB_ERR_ARG, "ptb_upload_scene: bad object kind");
+        if (o.reflect_type < 0 || o.reflect_type > 2) return fail(ctx, PTB_ERR_ARG, "ptb_upload_scene: bad reflect_type");
+        if (o.kind == PTB_OBJ_MESH && (o.tri_begin > desc->n_triangles || o.tri_count > desc->n_triangles - o.tri_begin))
+            return fail(ctx, PTB_ERR_ARG, "ptb_upload_scene: triangle range out of bounds");
+    }
+
+    // prio = rank in the reference's scan order: objects last-to-first (mod.rs:637), triangles first-to-last (mod.rs:558)
+    std::vector<uint32_t> prio_base(nobj, 0);
+    {
+        uint64_t run = 0;
+        for (size_t k = nobj; k-- > 0;) {
+            prio_base[k] = static_cast<uint32_t>(run);
+            run += desc->objects[k].kind == PTB_OBJ_SPHERE ? 1 : desc->objects[k].tri_count;
+        }
+        if (run >= 0xffffffffull) return fail(ctx, PTB_ERR_LIMIT, "ptb_upload_scene: too many primitives");
+    }
+
+    std::vector<float4> gate(nobj), mcol(nobj), memi(nobj);
+    for (size_t i = 0; i < nobj; ++i) {
+        const ptb_object &o = desc->objects[i];
+        gate[i] = f4(0, 0, 0, 0);
+        if (o.kind == PTB_OBJ_MESH) {
+            const V3 c = v3(o.bs_position) + v3(o.position);  // mod.rs:268
+            gate[i] = f4(c.x, c.y, c.z, o.bs_radius);
+        }
+        mcol[i] = f4(o.color[0], o.color[1], o.color[2], ibits(o.reflect_type));
+        const bool emits = o.emission[0] != 0.0f || o.emission[1] != 0.0f || o.emission[2] != 0.0f;
+        memi[i] = f4(o.emission[0], o.emission[1], o.emission[2], ibits(emits ? 1 : 0));
+    }
+
+    // split: which objects go to the BVH, which stay in the lock-step shared-memory list
+    std::vector<char> in_bvh(nobj, 0);
+    choose_bvh_objects(*desc, ctx->max_smem_optin, in_bvh);
+
+    std::vector<float4> lobj, ltri;
+    for (size_t k = nobj; k-- > 0;) {  // reverse index order = the reference's scan order
+        const ptb_object &o = desc->objects[k];
+        if (in_bvh[k]) continue;
+        if (o.kind == PTB_OBJ_SPHERE) {
+            lobj.push_back(f4(o.position[0], o.position[1], o.position[2], o.radius));
+            lobj.push_back(f4(ibits(0), ubits(prio_base[k]), ibits(0), ibits(static_cast<int32_t>(k))));
+        } else {
+            lobj.push_back(gate[k]);
+            lobj.push_back(f4(ibits(1), ibits(static_cast<int32_t>(ltri.size() / 3)), ibits(static_cast<int32_t>(o.tri_count)),
+                              ibits(static_cast<int32_t>(k))));
+            const V3 off = v3(o.position);
+            for (uint64_t j = 0; j < o.tri_count; ++j) {
+                const ptb_triangle &t = desc->triangles[o.tri_begin + j];
+                // Triangle::transformed then the edge vectors, exactly as per ray in mod.rs:559-561
+                const V3 a = v3(t.a) + off, b = v3(t.b) + off, c = v3(t.c) + off;
+                const V3 e1 = b - a, e2 = c - a;
+                ltri.push_back(f4(a.x, a.y, a.z, ibits(static_cast<int32_t>(k))));
+                ltri.push_back(f4(e1.x, e1.y, e1.z, ibits(static_cast<int32_t>(j))));
+                ltri.push_back(f4(e2.x, e2.y, e2.z, ubits(prio_base[k] + static_cast<uint32_t>(j))));
+            }
+        }
+    }
+    const size_t loose_bytes = (lobj.size() + ltri.size()) * sizeof(float4);
+    if (loose_bytes > ctx->max_smem_optin)
+        return fail(ctx, PTB_ERR_LIMIT, "ptb_upload_scene: loose primitive list does not fit in shared memory");
+
+    CU(ctx, ctx->loose_obj.upload(lobj, ctx->stream));
+    CU(ctx, ctx->loose_tri.upload(ltri, ctx->stream));
+    CU(ctx, ctx->obj_gate.upload(gate, ctx->stream));
+    CU(ctx, ctx->mat_color.upload(mcol, ctx->stream));
+    CU(ctx, ctx->mat_emis.upload(memi, ctx->stream));
+
+    DScene &ds = ctx->ds;
+    ds = DScene{};
+    ds.loose_obj = ctx->loose_obj.p; ds.loose_tri = ctx->loose_tri.p;
+    ds.n_loose_obj = static_cast<int>(lobj.size() / 2); ds.n_loose_tri = static_cast<int>(ltri.size() / 3);
+    ds.obj_gate = ctx->obj_gate.p; ds.mat_color = ctx->mat_color.p; ds.mat_emis = ctx->mat_emis.p;
+    ds.n_obj = static_cast<int>(nobj);
+    ds.bvh_root = BVH_EMPTY;
+
+    // camera frame, once per scene like render() (mod.rs:998-999; CameraData mod.rs:211-232)
+    {
+        const ptb_camera &c = desc->camera;
+        const V3 dir = v3(c.direction), pos = v3(c.position);
+        ds.sensor_origin = pos;
+        ds.lens_center = pos + dir * c.focal_length;
+        const V3 su = normalize(cross(dir, std::fabs(dir.y) < 0.9f ? mk3(0.f, 1.f, 0.f) : mk3(0.f, 0.f, 1.f)));
+        const V3 sv = cross(su, dir);
+        const float sensor_height = c.sensor_width / c.aspect_ratio;
+        ds.su = su * c.sensor_width;
+        ds.sv = sv * sensor_height;
+    }
+
+    const double t1 = now_ms();
+    double bvh_ms = 0.0;
+    ctx->stats.n_bvh_triangles = ctx->stats.n_bvh_spheres = ctx->stats.n_bvh_nodes = 0;
+    {
+        std::string berr;
+        cudaError_t e = bvh_build(*desc, in_bvh, prio_base, ctx->bvh, ds, ctx->stream, &bvh_ms, berr);
+        if (e != cudaSuccess) return cuda_fail(ctx, e, berr.empty() ? "bvh_build" : berr.c_str());
+        ctx->stats.n_bvh_triangles = ctx->bvh.n_tris;
+        ctx->stats.n_bvh_spheres = ctx->bvh.n_spheres;
+        ctx->stats.n_bvh_nodes = ctx->bvh.n_nodes;
+    }
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stats.upload_ms = (t1 - t0) + (now_ms() - t1 - bvh_ms > 0 ? now_ms() - t1 - bvh_ms : 0.0);
+    ctx->stats.bvh_build_ms = bvh_ms;
+    ctx->stats.n_loose_objects = static_cast<uint32_t>(ds.n_loose_obj);
+    ctx->stats.n_loose_triangles = static_cast<uint32_t>(ds.n_loose_tri);
+    ctx->has_scene = true;
+    return PTB_OK;
+}
+
+extern "C" int ptb_get_stats(const ptb_ctx *ctx, ptb_stats *out) {
+    if (!ctx || !out) return PTB_ERR_ARG;
+    if (ctx->stats_pending) {
+        ptb_ctx *m = const_cast<ptb_ctx *>(ctx);
+        CU(m, cudaSetDevice(ctx->device));
+        CU(m, cudaStreamSynchronize(ctx->pending_stream));
+        float ms = 0.f;
+        CU(m, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        unsigned long long seg = 0;
+        CU(m, cudaMemcpy(&seg, ctx->seg_counter.p, sizeof seg, cudaMemcpyDeviceToHost));
+        m->stats.render_ms = ms;
+        m->stats.segments = seg;
+        ctx->stats_pending = false;
+    }
+    *out = ctx->stats;
+    return PTB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// render
+// ------------------------------------------------------------------------------------------------
+extern "C" int ptb_render_device(ptb_ctx *ctx, int width, int height, uint64_t spp_begin, uint64_t spp_count, uint64_t seed,
+                                 float *d_sum_rgb, void *cuda_stream, const volatile int32_t *cancel,
+                                 volatile uint64_t *samples_done) {
+    if (!ctx) return fail(nullptr, PTB_ERR_ARG, "ptb_render_device: ctx is null");
+    if (!ctx->has_scene) return fail(ctx, PTB_ERR_STATE, "ptb_render_device: no scene uploaded");
+    if (width <= 0 || height <= 0 || !d_sum_rgb) return fail(ctx, PTB_ERR_ARG, "ptb_render_device: bad argument");
+    if (static_cast<uint64_t>(width) * static_cast<uint64_t>(height) > (1ull << 31) - 1)
+        return fail(ctx, PTB_ERR_LIMIT, "ptb_render_device: more than 2^31-1 pixels");
+    if (spp_begin + spp_count < spp_begin) return fail(ctx, PTB_ERR_ARG, "ptb_render_device: sample range overflows");
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);  // NULL = the legacy default stream, as in CUDA
+    const bool interactive = cancel != nullptr || samples_done != nullptr;
+
+    RenderArgs a{};
+    a.width = width; a.height = height; a.seed = seed; a.sum_rgb = d_sum_rgb;
+    a.tile_counter = ctx->tile_counter.p; a.segment_counter = ctx->seg_counter.p;
+    a.tiles_x = (width + TILE_W - 1) / TILE_W;
+    a.n_tiles = a.tiles_x * ((height + TILE_H - 1) / TILE_H);
+
+    ctx->stats.kernel_launches = 0;
+    ctx->stats.samples = 0;
+    CU(ctx, cudaMemsetAsync(ctx->seg_counter.p, 0, sizeof(unsigned long long), st));
+    CU(ctx, cudaEventRecord(ctx->ev0, st));
+    const uint64_t npix = static_cast<uint64_t>(width) * static_cast<uint64_t>(height);
+    // batch size: bounded work per launch so cancel / progress stay responsive (samples per launch ~ 2^31)
+    uint64_t batch = std::max<uint64_t>(1, (1ull << 31) / npix);
+    uint64_t done = 0;
+    int rc = PTB_OK;
+    while (done < spp_count) {
+        if (cancel && *cancel) { rc = PTB_CANCELLED; break; }
+        const uint64_t n = std::min(batch, spp_count - done);
+        a.spp_begin = spp_begin + done;
+        a.spp_count = n;
+        CU(ctx, cudaMemsetAsync(ctx->tile_counter.p, 0, sizeof(int), st));
+        CU(ctx, launch_render(ctx->ds, a, ctx->sm_count, st));
+        ctx->stats.kernel_launches++;
+        done += n;
+        if (interactive) {
+            CU(ctx, cudaStreamSynchronize(st));
+            if (samples_done) *samples_done = done * npix;
+        }
+    }
+    CU(ctx, cudaEventRecord(ctx->ev1, st));
+    ctx->stats.samples = done * npix;
+    if (interactive) {
+        CU(ctx, cudaStreamSynchronize(st));
+        float ms = 0.f;
+        CU(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        ctx->stats.render_ms = ms;
+        unsigned long long seg = 0;
+        CU(ctx, cudaMemcpy(&seg, ctx->seg_counter.p, sizeof seg, cudaMemcpyDeviceToHost));
+        ctx->stats.segments = seg;
+        ctx->stats_pending = false;
+    } else {
+        ctx->stats_pending = true;
+        ctx->pending_stream = st;
+    }
+    return rc;
+}
+
+extern "C" int ptb_resolve_device(ptb_ctx *ctx, const float *d_sum_rgb, uint64_t n_floats, uint64_t spp_total, float *d_mean_rgb,
+                                  void *cuda_stream) {
+    if (!ctx || !d_sum_rgb || !d_mean_rgb || spp_total == 0) return fail(ctx, PTB_ERR_ARG, "ptb_resolve_device: bad argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);  // NULL = the legacy default stream, as in CUDA
+    CU(ctx, launch_resolve(d_sum_rgb, n_floats, spp_total, d_mean_rgb, ctx->sm_count, st));
+    return PTB_OK;
+}
+
+extern "C" int ptb_render(ptb_ctx *ctx, int width, int height, uint64_t spp_begin, uint64_t spp_count, uint64_t seed, int out_kind,
+                          float *out_rgb, const volatile int32_t *cancel, volatile uint64_t *samples_done) {
+    if (!ctx) return fail(nullptr, PTB_ERR_ARG, "ptb_render: ctx is null");
+    if (!out_rgb || width <= 0 || height <= 0) return fail(ctx, PTB_ERR_ARG, "ptb_render: bad argument");
+    if (out_kind != PTB_OUT_MEAN && out_kind != PTB_OUT_SUM) return fail(ctx, PTB_ERR_ARG, "ptb_render: bad out_kind");
+    if (out_kind == PTB_OUT_MEAN && spp_count == 0) return fail(ctx, PTB_ERR_ARG, "ptb_render: spp_count is 0");
+    if (!ctx->has_scene) return fail(ctx, PTB_ERR_STATE, "ptb_render: no scene uploaded");
+    CU(ctx, cudaSetDevice(ctx->device));
+    const size_t nfl = static_cast<size_t>(width) * static_cast<size_t>(height) * 3;
+    CU(ctx, ctx->fb.resize(nfl));
+    CU(ctx, cudaMemsetAsync(ctx->fb.p, 0, nfl * sizeof(float), ctx->stream));
+    uint64_t progress = 0;
+    int rc = ptb_render_device(ctx, width, height, spp_begin, spp_count, seed, ctx->fb.p, ctx->stream, cancel,
+                               samples_done ? samples_done : &progress);
+    if (rc < 0) return rc;
+    const uint64_t spp_done = ctx->stats.samples / (static_cast<uint64_t>(width) * static_cast<uint64_t>(height));
+    if (out_kind == PTB_OUT_MEAN && spp_done > 0)
+        CU(ctx, launch_resolve(ctx->fb.p, nfl, rc == PTB_CANCELLED ? spp_done : spp_count, ctx->fb.p, ctx->sm_count, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(out_rgb, ctx->fb.p, nfl * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// parity hooks
+// ------------------------------------------------------------------------------------------------
+static int run_intersect(ptb_ctx *ctx, const float *rays6, uint64_t n, int pw, int ph, int32_t *obj, int32_t *tri, float *t,
+                         float *point3, float *normal3) {
+    if (!ctx->has_scene) return fail(ctx, PTB_ERR_STATE, "no scene uploaded");
+    if (!obj) return fail(ctx, PTB_ERR_ARG, "obj output is null");
+    if (n == 0) return PTB_OK;
+    CU(ctx, cudaSetDevice(ctx->device));
+    const size_t fl = (rays6 ? 6 * n : 0) + n + (point3 ? 3 * n : 0) + (normal3 ? 3 * n : 0);
+    CU(ctx, ctx->scratch_f.resize(fl + 4));
+    CU(ctx, ctx->scratch_i.resize(2 * n));
+    float *d_rays = nullptr, *d_t = ctx->scratch_f.p, *d_point = nullptr, *d_normal = nullptr;
+    size_t off = n;
+    if (rays6) { d_rays = ctx->scratch_f.p + off; off += 6 * n; }
+    if (point3) { d_point = ctx->scratch_f.p + off; off += 3 * n; }
+    if (normal3) { d_normal = ctx->scratch_f.p + off; off += 3 * n; }
+    int *d_obj = ctx->scratch_i.p, *d_tri = ctx->scratch_i.p + n;
+    cudaStream_t st = ctx->stream;
+    if (rays6) CU(ctx, cudaMemcpyAsync(d_rays, rays6, 6 * n * sizeof(float), cudaMemcpyHostToDevice, st));
+    CU(ctx, launch_intersect(ctx->ds, d_rays, n, pw, ph, d_obj, d_tri, d_t, d_point, d_normal, ctx->sm_count, st));
+    ctx->stats.kernel_launches = 1;
+    CU(ctx, cudaMemcpyAsync(obj, d_obj, n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (tri) CU(ctx, cudaMemcpyAsync(tri, d_tri, n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (t) CU(ctx, cudaMemcpyAsync(t, d_t, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (point3) CU(ctx, cudaMemcpyAsync(point3, d_point, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (normal3) CU(ctx, cudaMemcpyAsync(normal3, d_normal, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    return PTB_OK;
+}
+
+extern "C" int ptb_primary_hits(ptb_ctx *ctx, int width, int height, int32_t *obj, int32_t *tri, float *t) {
+    if (!ctx) return fail(nullptr, PTB_ERR_ARG, "ptb_primary_hits: ctx is null");
+    if (width <= 0 || height <= 0) return fail(ctx, PTB_ERR_ARG, "ptb_primary_hits: bad resolution");
+    return run_intersect(ctx, nullptr, static_cast<uint64_t>(width) * static_cast<uint64_t>(height), width, height, obj, tri, t,
+                         nullptr, nullptr);
+}
+
+extern "C" int ptb_intersect(ptb_ctx *ctx, const float *rays6, uint64_t n, int32_t *obj, int32_t *tri, float *t, float *point3,
+                             float *normal3) {
+    if (!ctx) return fail(nullptr, PTB_ERR_ARG, "ptb_intersect: ctx is null");
+    if (n && !rays6) return fail(ctx, PTB_ERR_ARG, "ptb_intersect: rays is null");
+    return run_intersect(ctx, rays6, n, 0, 0, obj, tri, t, point3, normal3);
+}

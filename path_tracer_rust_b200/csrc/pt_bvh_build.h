@@ -1,0 +1,29 @@
+// pt_bvh_build.h -- device BVH construction interface (internal)
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/ptb.h"
+#include "pt_device.cuh"
+
+namespace ptb {
+
+
+struct BvhDevice {
+    float4 *nodes = nullptr;
+    float4 *tris = nullptr;
+    float4 *spheres = nullptr;
+    unsigned n_nodes = 0, n_tris = 0, n_spheres = 0;
+    size_t cap_nodes = 0, cap_tris = 0, cap_spheres = 0;
+};
+
+// decides which objects are traversed through the BVH (in_bvh[k] = 1) and which stay in the shared-memory list
+void choose_bvh_objects(const ptb_scene_desc &desc, size_t max_smem_bytes, std::vector<char> &in_bvh);
+// builds the BVH over the chosen objects on the device and fills the bvh_* fields of `ds`
+cudaError_t bvh_build(const ptb_scene_desc &desc, const std::vector<char> &in_bvh, const std::vector<uint32_t> &prio_base,
+                      BvhDevice &out, DScene &ds, cudaStream_t st, double *build_ms, std::string &err);
+void bvh_release(BvhDevice &b);
+
+}  // namespace ptb

@@ -1,0 +1,352 @@
+// pt_kernels.cu -- sm_100a kernels of the radiance loop: closest hit, integrator megakernel, resolve.
+//
+// Replaces (reference, src/render/mod.rs): the rayon pixel loop :1001-1024, render_pixel :794-857,
+// radiance :661-792, intersect_scene :631-659, intersect_sphere :412-438, Triangle::intersect :554-615.
+//
+// Integrator design: persistent warps pull 8x4 pixel tiles from a global counter; one lane owns one
+// pixel and walks its samples in order (so the per-pixel fp32 sum has the reference's sequential
+// order and the image is deterministic).  A lane that finishes a path regenerates the next sample of
+// its pixel immediately, so lanes stay busy until the pixel's sample budget is used up.  The
+// "loose" part of the scene (few, large primitives: spheres, wall quads) is staged in shared memory
+// and scanned by all lanes in lock-step (broadcast LDS.128, no divergence); big meshes live in a
+// BVH (pt_bvh.cuh).  No tensor cores: there is no dense contraction in this workload.
+#include "pt_bvh.cuh"
+#include "pt_device.cuh"
+#include "pt_launch.h"
+
+namespace ptb {
+
+constexpr int KIND_SPHERE = 0;
+constexpr float PI_F = 3.141592653589793f;  // mod.rs:29
+constexpr int MAX_DEPTH = 12;               // mod.rs:661
+
+// ---------------------------------------------------------------------------------------------
+// closest hit over the shared-memory ("loose") object list, in the reference's scan order
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void closest_hit_loose(const float4 *__restrict__ s_obj, const float4 *__restrict__ s_tri,
+                                                  int n_obj, V3 o, V3 d, unsigned amask, Hit &best) {
+    for (int i = 0; i < n_obj; ++i) {
+        const float4 sph = s_obj[2 * i];
+        const float4 mb = s_obj[2 * i + 1];
+        const int kind = __float_as_int(mb.x);
+        const float t = sphere_t(xyz(sph), sph.w, o, d);
+        if (kind == KIND_SPHERE) {
+            if (t >= 0.0f && t < best.t) {
+                best.t = t;
+                best.prio = (uint32_t)__float_as_int(mb.y);
+                best.ref = REF_SPHERE_BIT | i;
+            }
+        } else {
+            // mesh: bounding-sphere gate first (mod.rs:267-277); skip the triangle scan if no lane passes
+            const bool pass = t >= 0.0f;
+            if (__any_sync(amask, pass)) {
+                const int k0 = __float_as_int(mb.y), k1 = k0 + __float_as_int(mb.z);
+                for (int k = k0; k < k1; ++k) {
+                    const float4 A = s_tri[3 * k], E1 = s_tri[3 * k + 1], E2 = s_tri[3 * k + 2];
+                    const float tt = triangle_t(xyz(A), xyz(E1), xyz(E2), o, d);
+                    if (pass && tt > 0.0f && tt < best.t) {
+                        best.t = tt;
+                        best.prio = (uint32_t)__float_as_int(E2.w);
+                        best.ref = k;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// resolves the winning primitive into (object id, triangle id, hit point, geometric normal)
+__device__ __forceinline__ void finish_hit(const DScene &sc, const float4 *__restrict__ s_obj, const float4 *__restrict__ s_tri,
+                                           const Hit &h, V3 o, V3 d, int &obj, int &tri, V3 &x, V3 &n) {
+    x = o + d * h.t;  // mod.rs:430 / :604
+    if (h.ref & REF_SPHERE_BIT) {
+        const int i = h.ref & (REF_SPHERE_BIT - 1);
+        float4 sph, mb;
+        if (h.ref & REF_BVH_BIT) { sph = __ldg(&sc.bvh_sph[2 * i]); mb = __ldg(&sc.bvh_sph[2 * i + 1]); obj = __float_as_int(mb.x); }
+        else { sph = s_obj[2 * i]; mb = s_obj[2 * i + 1]; obj = __float_as_int(mb.w); }
+        tri = -1;
+        n = normalize(x - xyz(sph));  // mod.rs:431
+    } else {
+        const int k = h.ref & (REF_SPHERE_BIT - 1);
+        float4 A, E1, E2;
+        if (h.ref & REF_BVH_BIT) { A = __ldg(&sc.bvh_tri[3 * k]); E1 = __ldg(&sc.bvh_tri[3 * k + 1]); E2 = __ldg(&sc.bvh_tri[3 * k + 2]); }
+        else { A = s_tri[3 * k]; E1 = s_tri[3 * k + 1]; E2 = s_tri[3 * k + 2]; }
+        obj = __float_as_int(A.w);
+        tri = __float_as_int(E1.w);
+        n = normalize(cross(xyz(E1), xyz(E2)));  // mod.rs:605
+    }
+}
+
+template <bool HAS_BVH>
+__device__ __forceinline__ Hit closest_hit(const DScene &sc, const float4 *__restrict__ s_obj, const float4 *__restrict__ s_tri,
+                                           V3 o, V3 d, unsigned amask) {
+    Hit best;
+    best.t = __int_as_float(0x7f800000);
+    best.prio = PRIO_NONE;
+    best.ref = REF_NONE;
+    closest_hit_loose(s_obj, s_tri, sc.n_loose_obj, o, d, amask, best);
+    if (HAS_BVH) bvh_closest_hit(sc, o, d, best);
+    return best;
+}
+
+__device__ __forceinline__ void stage_loose(const DScene &sc, float4 *smem, const float4 *&s_obj, const float4 *&s_tri) {
+    const int n0 = 2 * sc.n_loose_obj, n1 = 3 * sc.n_loose_tri;
+    for (int i = threadIdx.x; i < n0; i += blockDim.x) smem[i] = __ldg(&sc.loose_obj[i]);
+    for (int i = threadIdx.x; i < n1; i += blockDim.x) smem[n0 + i] = __ldg(&sc.loose_tri[i]);
+    __syncthreads();
+    s_obj = smem;
+    s_tri = smem + n0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// parity hooks: arbitrary rays / deterministic primary rays
+// ---------------------------------------------------------------------------------------------
+template <bool HAS_BVH>
+__global__ void __launch_bounds__(256) k_intersect(const DScene sc, const float *__restrict__ rays, unsigned long long n,
+                                                   int primary_w, int primary_h, int *__restrict__ obj_out,
+                                                   int *__restrict__ tri_out, float *__restrict__ t_out,
+                                                   float *__restrict__ point_out, float *__restrict__ normal_out) {
+    extern __shared__ float4 smem[];
+    const float4 *s_obj, *s_tri;
+    stage_loose(sc, smem, s_obj, s_tri);
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const unsigned long long n_round = (n + 31ull) & ~31ull;  // whole warps stay converged for the votes
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        const bool valid = i < n;
+        V3 o = mk3(0.f, 0.f, 0.f), d = mk3(0.f, 0.f, 1.f);
+        if (valid) {
+            if (rays) {
+                o = mk3(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]);
+                d = mk3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]);
+            } else {  // centre ray of pixel i: xsub = ysub = xfilter = yfilter = 0 (mod.rs:805-843)
+                const int row = (int)(i / (unsigned)primary_w), x = (int)(i % (unsigned)primary_w);
+                camera_ray(sc, primary_w, primary_h, x, primary_h - 1 - row, 0.f, 0.f, 0.f, 0.f, o, d);
+            }
+        }
+        const Hit h = closest_hit<HAS_BVH>(sc, s_obj, s_tri, o, d, 0xffffffffu);
+        if (valid) {
+            int obj = -1, tri = -1;
+            V3 x = mk3(0.f, 0.f, 0.f), nn = mk3(0.f, 0.f, 0.f);
+            float t = 0.f;
+            if (h.ref != REF_NONE) { finish_hit(sc, s_obj, s_tri, h, o, d, obj, tri, x, nn); t = h.t; }
+            obj_out[i] = obj;
+            if (tri_out) tri_out[i] = tri;
+            if (t_out) t_out[i] = t;
+            if (point_out) { point_out[3 * i] = x.x; point_out[3 * i + 1] = x.y; point_out[3 * i + 2] = x.z; }
+            if (normal_out) { normal_out[3 * i] = nn.x; normal_out[3 * i + 1] = nn.y; normal_out[3 * i + 2] = nn.z; }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the integrator megakernel
+// ---------------------------------------------------------------------------------------------
+struct PathStackEntry { V3 o, d, T; int depth; };
+
+template <bool HAS_BVH>
+__global__ void __launch_bounds__(RENDER_THREADS, RENDER_MIN_BLOCKS) k_render(const DScene sc, const RenderArgs a) {
+    extern __shared__ float4 smem[];
+    const float4 *s_obj, *s_tri;
+    stage_loose(sc, smem, s_obj, s_tri);
+
+    const int lane = threadIdx.x & 31;
+    const int W = a.width, H = a.height;
+    const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
+    unsigned long long n_segments = 0;
+
+    for (;;) {
+        int tile = 0;
+        if (lane == 0) tile = atomicAdd(a.tile_counter, 1);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= a.n_tiles) break;
+        const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
+        const int px = tx * TILE_W + (lane & (TILE_W - 1)), row = ty * TILE_H + (lane / TILE_W);
+        const bool valid = px < W && row < H;
+        const uint32_t pixel = (uint32_t)row * (uint32_t)W + (uint32_t)px;
+        const int y = H - 1 - row;  // mod.rs:805
+        float *fb = a.sum_rgb + 3ull * pixel;
+        V3 acc = mk3(0.f, 0.f, 0.f);
+        if (valid) acc = mk3(fb[0], fb[1], fb[2]);
+
+        unsigned long long s = a.spp_begin;
+        const unsigned long long s_end = a.spp_begin + a.spp_count;
+        bool active = valid && s < s_end;
+        bool need_new = true;
+        V3 o = mk3(0.f, 0.f, 0.f), d = mk3(0.f, 0.f, 1.f), T = mk3(1.f, 1.f, 1.f), L = mk3(0.f, 0.f, 0.f);
+        int depth = 0, sp = 0;
+        uint32_t event = 0, nseg = 0;
+        PathStackEntry stk[2];
+
+        for (;;) {
+            const unsigned amask = __ballot_sync(0xffffffffu, active);
+            if (amask == 0u) break;
+            if (active) {
+                uint32_t rnd[4];
+                if (need_new) {  // camera sample: event 0, slots 0,1 (mod.rs:814-843)
+                    philox4x32_10(pixel, (uint32_t)s, (uint32_t)(s >> 32), 0u, k0, k1, rnd);
+                    const float ysub = (float)((s / 2) % 2), xsub = (float)(s % 2);
+                    const float r1 = 2.0f * u32_to_unit(rnd[0]);
+                    const float r2 = 2.0f * u32_to_unit(rnd[1]);
+                    camera_ray(sc, W, H, px, y, xsub, ysub, tent(r1), tent(r2), o, d);
+                    T = mk3(1.f, 1.f, 1.f); L = mk3(0.f, 0.f, 0.f);
+                    depth = 0; sp = 0; event = 0;
+                    need_new = false;
+                }
+                // ---- one radiance() call (mod.rs:662): event k, slots 0 = RR, 1,2 = diffuse, 3 = refraction choice
+                event++;
+                nseg++;
+                philox4x32_10(pixel, (uint32_t)s, (uint32_t)(s >> 32), event, k0, k1, rnd);
+                const Hit h = closest_hit<HAS_BVH>(sc, s_obj, s_tri, o, d, amask);
+                bool cont = false;
+                if (h.ref != REF_NONE) {
+                    int obj, tri;
+                    V3 x, n;
+                    finish_hit(sc, s_obj, s_tri, h, o, d, obj, tri, x, n);
+                    const float4 mc = __ldg(&sc.mat_color[obj]);
+                    const float4 me = __ldg(&sc.mat_emis[obj]);
+                    const int refl = __float_as_int(mc.w);
+                    V3 color = xyz(mc);
+                    const float max_reflection = fmaxf(color.x, fmaxf(color.y, color.z));
+                    const V3 nl = dot(n, d) < 0.0f ? n : n * -1.0f;
+                    const int new_depth = depth + 1;
+                    bool alive = true;
+                    if (new_depth > 5) {  // Russian roulette, mod.rs:677-683
+                        if (u32_to_unit(rnd[0]) < max_reflection && new_depth < MAX_DEPTH) color = color * PTB_RCP(max_reflection);
+                        else alive = false;
+                    }
+                    if (__float_as_int(me.w)) L = L + T * xyz(me);
+                    if (alive) {
+                        const V3 Tc = T * color;
+                        if (refl == 0) {  // Diffuse, mod.rs:687-715
+                            const float r1 = 2.0f * PI_F * u32_to_unit(rnd[1]);
+                            const float r2 = u32_to_unit(rnd[2]);
+                            const float r2s = PTB_SQRT(r2);
+                            const V3 w = nl;
+                            const V3 u = normalize(cross(fabsf(w.x) > 0.1f ? mk3(0.f, 1.f, 0.f) : mk3(1.f, 0.f, 0.f), w));
+                            const V3 v = cross(w, u);
+                            float sn, cs;
+                            sincos_det(r1, sn, cs);
+                            d = normalize(u * cs * r2s + v * sn * r2s + w * PTB_SQRT(1.0f - r2));
+                            T = Tc;
+                        } else {
+                            const V3 rd = d - n * 2.0f * dot(n, d);  // mod.rs:722-723
+                            if (refl == 1) {  // Specular
+                                d = rd; T = Tc;
+                            } else {  // Refract, mod.rs:729-788
+                                const bool into = dot(n, nl) > 0.0f;
+                                const float nnt = into ? PTB_DIV(1.0f, 1.5f) : PTB_DIV(1.5f, 1.0f);
+                                const float ddn = dot(d, nl);
+                                const float cos2t = 1.0f - nnt * nnt * (1.0f - ddn * ddn);
+                                if (cos2t < 0.0f) {  // total internal reflection
+                                    d = rd; T = Tc;
+                                } else {
+                                    const V3 tdir = normalize(d * nnt - n * ((into ? 1.0f : -1.0f) * (ddn * nnt + PTB_SQRT(cos2t))));
+                                    const float r0 = PTB_DIV(0.5f * 0.5f, 2.5f * 2.5f);
+                                    const float c = 1.0f - (into ? -ddn : dot(tdir, n));
+                                    const float c2 = c * c;
+                                    const float re = r0 + (1.0f - r0) * (c * (c2 * c2));
+                                    const float tr = 1.0f - re;
+                                    const float p = 0.25f + 0.5f * re;
+                                    if (new_depth > 2) {
+                                        if (u32_to_unit(rnd[3]) < p) { T = Tc * PTB_DIV(re, p); d = rd; }
+                                        else { T = Tc * PTB_DIV(tr, 1.0f - p); d = tdir; }
+                                    } else {  // deterministic two-way split, reflection first (mod.rs:776-785)
+                                        stk[sp].o = x; stk[sp].d = tdir; stk[sp].T = Tc * tr; stk[sp].depth = new_depth;
+                                        sp++;
+                                        T = Tc * re; d = rd;
+                                    }
+                                }
+                            }
+                        }
+                        o = x;
+                        depth = new_depth;
+                        cont = true;
+                    }
+                }
+                if (!cont) {
+                    if (sp > 0) {
+                        sp--;
+                        o = stk[sp].o; d = stk[sp].d; T = stk[sp].T; depth = stk[sp].depth;
+                    } else {  // sample finished: radiance_v += radiance (mod.rs:846)
+                        acc = acc + L;
+                        s++;
+                        if (s < s_end) need_new = true; else active = false;
+                    }
+                }
+            }
+        }
+        if (valid) { fb[0] = acc.x; fb[1] = acc.y; fb[2] = acc.z; }
+        n_segments += nseg;
+    }
+    // one atomic per warp
+    for (int off = 16; off > 0; off >>= 1) n_segments += __shfl_down_sync(0xffffffffu, n_segments, off);
+    if (lane == 0 && n_segments) atomicAdd(a.segment_counter, n_segments);
+}
+
+// radiance / spp, clamp to [0,1] (mod.rs:849-856)
+__global__ void k_resolve(const float *__restrict__ sum, unsigned long long n, float spp, float *__restrict__ mean) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float v = PTB_DIV(sum[i], spp);
+        mean[i] = fminf(fmaxf(v, 0.0f), 1.0f);
+    }
+}
+
+// a*b+c with operands chosen so that a fused multiply-add gives a different answer
+__global__ void k_contraction_probe(float a, float b, float c, float *out) { out[0] = a * b + c; }
+
+// ---------------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------------
+static size_t loose_smem_bytes(const DScene &sc) { return sizeof(float4) * (2ull * sc.n_loose_obj + 3ull * sc.n_loose_tri); }
+
+cudaError_t launch_contraction_probe(float a, float b, float c, float *d_out, cudaStream_t st) {
+    k_contraction_probe<<<1, 1, 0, st>>>(a, b, c, d_out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_intersect(const DScene &sc, const float *d_rays, unsigned long long n, int pw, int ph, int *d_obj, int *d_tri,
+                             float *d_t, float *d_point, float *d_normal, int sm_count, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    const size_t smem = loose_smem_bytes(sc);
+    const bool bvh = sc.bvh_root != BVH_EMPTY;
+    auto kern = bvh ? k_intersect<true> : k_intersect<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    unsigned long long blocks = (n + 255) / 256;
+    const unsigned long long cap = (unsigned long long)sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    kern<<<(unsigned)blocks, 256, smem, st>>>(sc, d_rays, n, pw, ph, d_obj, d_tri, d_t, d_point, d_normal);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_render(const DScene &sc, const RenderArgs &a, int sm_count, cudaStream_t st) {
+    const size_t smem = loose_smem_bytes(sc);
+    const bool bvh = sc.bvh_root != BVH_EMPTY;
+    auto kern = bvh ? k_render<true> : k_render<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, RENDER_THREADS, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    // persistent grid: a whole number of resident CTAs per SM (148 SMs on B200)
+    long long blocks = (long long)sm_count * per_sm;
+    const long long need = ((long long)a.n_tiles + RENDER_THREADS / 32 - 1) / (RENDER_THREADS / 32);
+    if (blocks > need) blocks = need;
+    if (blocks < 1) blocks = 1;
+    kern<<<(unsigned)blocks, RENDER_THREADS, smem, st>>>(sc, a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_resolve(const float *d_sum, unsigned long long n, unsigned long long spp, float *d_mean, int sm_count,
+                           cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    unsigned long long blocks = (n + 255) / 256;
+    const unsigned long long cap = (unsigned long long)sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    k_resolve<<<(unsigned)blocks, 256, 0, st>>>(d_sum, n, (float)spp, d_mean);
+    return cudaGetLastError();
+}
+
+}  // namespace ptb

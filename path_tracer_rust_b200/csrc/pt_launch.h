@@ -1,0 +1,32 @@
+// pt_launch.h -- host-visible launch interface of pt_kernels.cu / pt_bvh_build.cu (internal, not part of the C ABI)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pt_device.cuh"
+
+namespace ptb {
+
+constexpr int TILE_W = 8, TILE_H = 4;  // one warp = one 8x4 pixel tile
+constexpr int RENDER_THREADS = 256;
+constexpr int RENDER_MIN_BLOCKS = 2;
+constexpr int BVH_EMPTY = -1;
+
+struct RenderArgs {
+    int width, height;
+    unsigned long long spp_begin, spp_count;
+    unsigned long long seed;
+    float *sum_rgb;                        // W*H*3 fp32 running sum, reference index order
+    int *tile_counter;                     // zeroed before each launch
+    int n_tiles, tiles_x;
+    unsigned long long *segment_counter;   // += closest-hit queries
+};
+
+cudaError_t launch_contraction_probe(float a, float b, float c, float *d_out, cudaStream_t st);
+cudaError_t launch_intersect(const DScene &sc, const float *d_rays, unsigned long long n, int pw, int ph, int *d_obj, int *d_tri,
+                             float *d_t, float *d_point, float *d_normal, int sm_count, cudaStream_t st);
+cudaError_t launch_render(const DScene &sc, const RenderArgs &a, int sm_count, cudaStream_t st);
+cudaError_t launch_resolve(const float *d_sum, unsigned long long n, unsigned long long spp, float *d_mean, int sm_count,
+                           cudaStream_t st);
+
+}  // namespace ptb

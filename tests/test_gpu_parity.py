@@ -1,0 +1,190 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle.  Run on the B200 box: pytest -m gpu."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from conftest import SCENES, scene_path, sphere_obj
+
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+
+
+@pytest.fixture(scope="module")
+def be():
+    import path_tracer_rust_b200 as P
+    b = P.Backend(0)
+    yield b
+    b.close()
+
+
+def load_both(be, sid_or_path):
+    import path_tracer_rust_b200 as P
+    path = sid_or_path if sid_or_path.endswith(".json") else scene_path(sid_or_path)
+    sc = P.Scene.load(path)
+    be.upload_scene(sc)
+    return sc, O.OracleScene(path)
+
+
+def bits(a):
+    return np.ascontiguousarray(a, f32).view(np.uint32)
+
+
+# ---- known answers of the reference's own tests, through the CUDA kernels (test.rs:43-144) ------------------
+def test_reference_sphere_kats_on_gpu(be, kat_scene):
+    load_both(be, kat_scene([sphere_obj((0, 0, -3))], "k1"))
+    obj, tri, t, pt, n = be.intersect(np.array([[0, 0, 0, 0, 0, -1], [0, 1, 0, 0, 0, -1],
+                                                [2, 0, 0, math.sqrt(0.5), 0, -math.sqrt(0.5)]], f32))
+    assert obj.tolist() == [0, 0, -1] and tri.tolist() == [-1, -1, -1]
+    assert t[:2].tolist() == [2.0, 3.0]
+    assert pt[0].tolist() == [0, 0, -2] and n[0].tolist() == [0, 0, 1]
+    assert pt[1].tolist() == [0, 1, -3] and n[1].tolist() == [0, 1, 0]
+    load_both(be, kat_scene([sphere_obj((0, 0, 0))], "k2"))
+    obj, tri, t, pt, n = be.intersect(np.array([[0, 0, 0, 0, 0, -1]], f32))
+    assert (obj[0], t[0], pt[0].tolist(), n[0].tolist()) == (0, 1.0, [0, 0, -1], [0, 0, -1])
+
+
+# ---- (1) deterministic primary rays: indices identical, t bit-identical -------------------------------------
+@pytest.mark.parametrize("sid", SCENES)
+@pytest.mark.parametrize("res", [(192, 128), (450, 300)])
+def test_primary_hits_bit_exact(be, sid, res):
+    _, osc = load_both(be, sid)
+    W, H = res
+    g_obj, g_tri, g_t = be.primary_hits(W, H)
+    o_obj, o_tri, o_t = osc.primary_hits(W, H)
+    assert np.array_equal(g_obj, o_obj)
+    assert np.array_equal(g_tri, o_tri)
+    assert np.array_equal(bits(g_t), bits(o_t))          # criterion allows 1e-5 rel; we get bit-identical
+    assert (g_obj >= 0).any() or sid == "none"
+
+
+# ---- (2) arbitrary rays, including rays that start on surfaces (self-hit behaviour) ----------
+def random_rays(rng, n, extent=3.0):
+    o = rng.uniform(-extent, extent, (n, 3)).astype(f32)
+    d = rng.normal(size=(n, 3)).astype(f32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True).astype(f32)
+    return np.concatenate([o, d.astype(f32)], 1)
+
+
+@pytest.mark.parametrize("sid", SCENES)
+def test_intersect_arbitrary_rays_bit_exact(be, sid):
+    _, osc = load_both(be, sid)
+    rng = np.random.default_rng(1234)
+    rays = random_rays(rng, 200_000)
+    g = be.intersect(rays)
+    o = osc.intersect(rays)
+    for a, b in zip(g, o):
+        assert np.array_equal(bits(a) if a.dtype == f32 else a, bits(b) if b.dtype == f32 else b)
+    # second generation: start exactly on the hit points, cosine-ish random directions
+    hit = o[0] >= 0
+    if hit.sum() > 100:
+        d2 = rng.normal(size=(int(hit.sum()), 3)).astype(f32)
+        d2 /= np.linalg.norm(d2, axis=1, keepdims=True).astype(f32)
+        rays2 = np.concatenate([o[3][hit], d2.astype(f32)], 1)
+        g2 = be.intersect(rays2)
+        o2 = osc.intersect(rays2)
+        for a, b in zip(g2, o2):
+            assert np.array_equal(bits(a) if a.dtype == f32 else a, bits(b) if b.dtype == f32 else b)
+
+
+# ---- (3) lock-step images: same counter RNG, same sin/cos -> bit-identical sum framebuffer ------------------
+@pytest.mark.parametrize("sid,W,H,spp", [("cornell", 96, 64, 16), ("mesh", 60, 40, 4), ("single-sphere", 96, 64, 8),
+                                         ("two-spheres", 96, 64, 8), ("three-spheres", 96, 64, 8), ("cartesian", 48, 32, 4),
+                                         ("cornell", 37, 23, 5)])
+def test_lockstep_framebuffer_bit_exact(be, sid, W, H, spp):
+    import path_tracer_rust_b200.api as A
+    _, osc = load_both(be, sid)
+    g = be.render(W, H, spp, seed=42, out_kind=A.PTB_OUT_SUM)
+    o, ost = osc.render_sum(W, H, spp, seed=42, rng=O.RNG_PHILOX, sincos=O.SINCOS_DET, accum=O.ACCUM_FORWARD)
+    st = be.stats()
+    assert st["segments"] == int(ost[0])                 # identical path geometry
+    assert st["samples"] == W * H * spp
+    assert np.array_equal(bits(g), bits(o))
+    gm = be.render(W, H, spp, seed=42, out_kind=A.PTB_OUT_MEAN)
+    assert np.array_equal(bits(gm), bits(O.resolve(o, spp)))
+
+
+def test_batch_and_offset_invariance(be):
+    import path_tracer_rust_b200.api as A
+    _, osc = load_both(be, "cornell")
+    W, H = 64, 40
+    full = be.render(W, H, 12, seed=9, out_kind=A.PTB_OUT_SUM)
+    a = be.render(W, H, 5, spp_begin=0, seed=9, out_kind=A.PTB_OUT_SUM)
+    b = be.render(W, H, 7, spp_begin=5, seed=9, out_kind=A.PTB_OUT_SUM)
+    o_b, _ = osc.render_sum(W, H, 7, spp_begin=5, seed=9)
+    assert np.array_equal(bits(b), bits(o_b))            # global sample indices: shard-invariant streams
+    np.testing.assert_allclose(a + b, full, rtol=1e-5, atol=1e-6)
+    assert not np.array_equal(full, be.render(W, H, 12, seed=10, out_kind=A.PTB_OUT_SUM))
+
+
+# ---- (4) images against the reference's own behaviour (sequential RNG, libm sin/cos, recursive radiance) ----
+@pytest.mark.parametrize("sid,W,H,spp", [("cornell", 120, 80, 256), ("three-spheres", 120, 80, 64), ("mesh", 60, 40, 64)])
+def test_image_statistics_match_reference_mode(be, sid, W, H, spp):
+    """Stated tolerance: per channel RMSE(gpu, ref) <= 1.25 * RMSE(ref_seedA, ref_seedB) and
+    |mean_gpu - mean_ref| / mean_ref <= 1 % at equal spp (unclamped means)."""
+    import path_tracer_rust_b200.api as A
+    _, osc = load_both(be, sid)
+    g = be.render(W, H, spp, seed=1, out_kind=A.PTB_OUT_SUM) / f32(spp)
+    ref = dict(rng=O.RNG_SEQ, sincos=O.SINCOS_LIBM, accum=O.ACCUM_RECURSIVE)
+    ra = osc.render_sum(W, H, spp, seed=100, **ref)[0] / f32(spp)
+    rb = osc.render_sum(W, H, spp, seed=200, **ref)[0] / f32(spp)
+    for c in range(3):
+        noise = math.sqrt(float(np.mean((ra[:, c] - rb[:, c]) ** 2)))
+        err = math.sqrt(float(np.mean((g[:, c] - ra[:, c]) ** 2)))
+        assert err <= 1.25 * noise + 1e-7, (sid, c, err, noise)
+        m_ref = 0.5 * (float(ra[:, c].mean()) + float(rb[:, c].mean()))
+        if m_ref > 1e-4:
+            assert abs(float(g[:, c].mean()) - m_ref) / m_ref <= 0.01, (sid, c)
+
+
+def test_exact_images(be):
+    import path_tracer_rust_b200.api as A
+    load_both(be, "cartesian")
+    assert not be.render(96, 64, 8, seed=3).any()        # no emitter: exactly black
+    _, osc = load_both(be, "single-sphere")
+    W, H, spp = 96, 64, 8
+    img = be.render(W, H, spp, seed=3).reshape(H, W, 3)
+    inside = (osc.primary_hits(W, H)[0].reshape(H, W) == 0)
+    core = np.zeros_like(inside)
+    core[1:-1, 1:-1] = (inside[1:-1, 1:-1] & inside[:-2, 1:-1] & inside[2:, 1:-1] & inside[1:-1, :-2] & inside[1:-1, 2:]
+                        & inside[:-2, :-2] & inside[2:, 2:] & inside[:-2, 2:] & inside[2:, :-2])
+    assert core.sum() > 50 and (img[core] == 1.0).all()
+
+
+# ---- behaviour of the boundary --------------------------------------------------------------------------------
+def test_api_errors_and_cancel(kat_scene):
+    import path_tracer_rust_b200 as P
+    import path_tracer_rust_b200.api as A
+    b = P.Backend(0)
+    try:
+        with pytest.raises(P.BackendError) as e:
+            b.render(8, 8, 1)
+        assert e.value.code == -5                          # PTB_ERR_STATE: no scene yet
+        b.upload_scene(P.Scene.load(scene_path("cornell")))
+        with pytest.raises(P.BackendError) as e:
+            b.render(0, 8, 1)
+        assert e.value.code == -1
+        cancel = C.c_int32(1)
+        done = C.c_uint64(123)
+        out = b.render(16, 16, 4, cancel=cancel, samples_done=done, out_kind=A.PTB_OUT_SUM)
+        assert b.last_rc == A.PTB_CANCELLED and not out.any()
+    finally:
+        b.close()
+    with pytest.raises(P.BackendError):
+        P.Backend(9999)
+
+
+def test_render_mirror_of_reference_api(be):
+    """render(RenderConfig, progress sink, cancel flag) -> RenderDone{image, duration}  (mod.rs:928-934)"""
+    import path_tracer_rust_b200 as P
+    updates = []
+    cfg = P.RenderConfig(samples_per_pixel=8, resolution=P.Resolution(height=60, width=90), scene=P.Scene.load("cornell"), seed=5)
+    done = P.render(cfg, send_update_progress=updates.append, backend=be)
+    assert done.image.pixels.shape == (90 * 60, 3) and done.image.pixels.max() <= 1.0 and done.image.pixels.min() >= 0.0
+    assert done.duration > 0 and done.image.hash != 0
+    rgb = done.image.display_rgb8()
+    assert rgb.shape == (60, 90, 3)
+    # ceiling light is at the top of the displayed image, floor at the bottom (SURVEY.md 8a orientation)
+    assert rgb[:5].mean() > rgb[-5:].mean()

@@ -1,0 +1,165 @@
+"""CPU-only tests: the C-ABI library loads and exports what include/ptb.h declares, the host scene loader agrees with
+the oracle's independent loader, the output helpers match the reference's known answers, and the N>1 sharding logic
+works over gloo.  No compute call is made (there is no GPU here and no CPU fallback in the product)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from conftest import ROOT, SCENES, scene_path
+
+f32 = np.float32
+
+
+@pytest.fixture(scope="module")
+def P():
+    import __graft_entry__ as g
+    if not os.path.exists(os.path.join(ROOT, "path_tracer_rust_b200", "libptb.so")):
+        g.build()
+    import path_tracer_rust_b200 as P
+    return P
+
+
+def test_library_exports_every_declared_symbol(P):
+    hdr = open(os.path.join(ROOT, "include", "ptb.h")).read()
+    declared = sorted(set(re.findall(r"\b(ptb_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 19
+    L = P.load_library()
+    for name in declared:
+        assert hasattr(L, name), name
+    import path_tracer_rust_b200.api as A
+    assert sorted(A.ABI_SYMBOLS) == declared
+    assert L.ptb_abi_version() == 1
+
+
+def test_no_cpu_fallback(P):
+    if P.load_library().ptb_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(P.BackendError, match="no CUDA device"):
+        P.Backend(0)
+
+
+def test_product_never_touches_the_oracle():
+    pkg = os.path.join(ROOT, "path_tracer_rust_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")) or fn == "Makefile":
+                txt = open(os.path.join(dirpath, fn), errors="ignore").read()
+                assert "oracle_lib" not in txt and "pt_oracle" not in txt and "oracle/" not in txt, fn
+    out = subprocess.run(["ldd", os.path.join(pkg, "libptb.so")], capture_output=True, text=True).stdout
+    assert "oracle" not in out
+
+
+@pytest.mark.parametrize("sid", SCENES)
+def test_host_loader_matches_oracle_loader(P, sid):
+    """Two independent JSON/OFF readers must produce bit-identical scene data."""
+    sc = P.Scene.load(sid)
+    osc = O.OracleScene(scene_path(sid))
+    c = osc.counts()
+    assert sc.n_objects == c["objects"] and sc.n_triangles == c["triangles"] and sc.id == osc.id
+    for i, o in enumerate(sc.objects()):
+        if o.kind == 1:
+            p, r = osc.mesh_bounds(i)
+            assert list(o.bs_position) == p.tolist() and f32(o.bs_radius) == r
+
+
+def test_loader_error_behaviour(P, tmp_path):
+    with pytest.raises(P.BackendError) as e:
+        P.Scene.load(str(tmp_path / "missing.json"))
+    assert e.value.code == -3
+    bad = tmp_path / "bad.json"
+    bad.write_text('{"id": "x", "objects": [{"type_": {"Cube": {}}, "position": [0,0,0], "material": '
+                   '{"color": [1,1,1], "emmission": [0,0,0], "reflect_type": "Diffuse"}}], "camera": '
+                   '{"position": [0,0,0], "direction": [0,0,-1], "focal_length": 0.035, "sensor_width": 0.036, "aspect_ratio": 1.5}}')
+    with pytest.raises(P.BackendError, match="unknown variant `Cube`"):
+        P.Scene.load(str(bad))
+    hd = tmp_path / "hd.json"
+    hd.write_text('{"id": "hd", "objects": [{"type_": {"MeshFile": {"path": "meshes/hdodec.off", "scale": 1.0}}, "position": [0,0,0], '
+                  '"material": {"color": [1,1,1], "emmission": [0,0,0], "reflect_type": "Diffuse"}}], "camera": '
+                  '{"position": [0,0,0], "direction": [0,0,-1], "focal_length": 0.035, "sensor_width": 0.036, "aspect_ratio": 1.5}}')
+    with pytest.raises(P.BackendError, match="Invalid face"):   # load_off.rs:73-76: pentagons are rejected
+        P.Scene.load(str(hd), base_dir=ROOT)
+
+
+def test_gamma_and_ppm(P, tmp_path):
+    assert [P.to_int_with_gamma_correction(x) for x in (0.0, 0.5, 0.75, 1.0)] == [0, 186, 224, 255]   # test.rs:29-35
+    for x in np.linspace(-0.5, 1.5, 2001):
+        assert P.to_int_with_gamma_correction(float(x)) == O.gamma_u8(float(x))
+    import path_tracer_rust_b200.api as A
+    W, H = 3, 2
+    px = np.arange(W * H * 3, dtype=f32).reshape(-1, 3) / f32(W * H * 3)
+    img = A.Image(pixels=px, resolution=A.Resolution(height=H, width=W), hash=0)
+    path = tmp_path / "a.ppm"
+    A.write_ppm(str(path), img, spp=7, scene_id="cornell", seconds=3)
+    txt = path.read_text()
+    lines = txt.split("\n")
+    assert lines[0] == "P3" and lines[1] == "# samplesPerPixel: 7, resolution_y: 2, scene_id: cornell"
+    assert lines[2] == "# rendering time: 3 s" and lines[3] == "3 2" and lines[4] == "255"
+    vals = [int(v) for v in lines[5].split()]
+    expect = [O.gamma_u8(float(v)) for p in px[::-1] for v in p]                       # reversed pixel order, mod.rs:1065
+    assert vals == expect and lines[5].endswith(" ")
+    opath = tmp_path / "o.ppm"
+    O.lib().pto_write_ppm(str(opath).encode(), O._fp(np.ascontiguousarray(px)), W, H, 7, b"cornell", 3)
+    assert opath.read_text() == txt
+
+
+def test_siphash13_pixel_hash(P):
+    import path_tracer_rust_b200.api as A
+    # SipHash-1-3, zero key, empty input (Rust: DefaultHasher::new().finish())
+    assert A.hash_pixels(np.zeros((0, 3), f32)) == 15130871412783076140
+    a = np.arange(30, dtype=f32).reshape(10, 3)
+    assert A.hash_pixels(a) != A.hash_pixels(a[::-1].copy())
+
+
+def test_shard_samples_partition():
+    from path_tracer_rust_b200.distributed import shard_samples
+    for spp in (0, 1, 7, 256, 4096, 1000003):
+        for G in (1, 2, 3, 4, 8):
+            spans = [shard_samples(spp, G, g) for g in range(G)]
+            assert spans[0][0] == 0 and sum(c for _, c in spans) == spp
+            for (b0, c0), (b1, _) in zip(spans, spans[1:]):
+                assert b0 + c0 == b1
+            assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
+    with pytest.raises(ValueError):
+        shard_samples(8, 2, 2)
+
+
+_GLOO_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import numpy as np, torch, torch.distributed as dist
+import oracle_lib as O
+from path_tracer_rust_b200.distributed import render_sharded
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+W, H, SPP = 40, 24, 10
+osc = O.OracleScene(os.path.join({root!r}, "scenes", "cornell.json"))
+class FakeShard:                       # host-logic test double: the oracle stands in for the GPU kernels
+    def render_sum(self, b, c):
+        return torch.from_numpy(osc.render_sum(W, H, c, spp_begin=b, seed=77)[0].reshape(-1).copy())
+    def resolve(self, fb, spp):
+        return torch.from_numpy(O.resolve(fb.numpy(), spp))
+img = render_sharded(FakeShard(), SPP, rank, world)
+if rank == 0:
+    full = O.resolve(osc.render_sum(W, H, SPP, seed=77)[0], SPP).reshape(-1)
+    np.testing.assert_allclose(img.numpy(), full, rtol=1e-5, atol=1e-6)
+    print("SHARD_OK", float(img.mean()))
+else:
+    assert img is None
+dist.destroy_process_group()
+"""
+
+
+def test_sharded_render_world_size_2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29613")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29613", str(script)], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "SHARD_OK" in r.stdout

@@ -102,6 +102,10 @@ const char *ptb_last_error(const ptb_ctx *ctx); /* ctx may be NULL: last error o
  * triangles A'=a+pos, E1, E2 with the reference's own roundings), uploads, builds the device BVH. */
 int ptb_upload_scene(ptb_ctx *ctx, const ptb_scene_desc *desc);
 int ptb_get_stats(const ptb_ctx *ctx, ptb_stats *out);
+/* Tuning knobs, effective from the next ptb_upload_scene (results never depend on them, only speed):
+ *   "bvh_min_tris"    meshes with at least this many triangles are traversed through the BVH (default 24; a huge value = brute force)
+ *   "bvh_min_spheres" scenes with at least this many spheres put them in the BVH (default 48) */
+int ptb_set_option(ptb_ctx *ctx, const char *key, double value);
 
 /* ---- the hot path: replaces the rayon loop + render_pixel + radiance (mod.rs:1001-1024, 794-857, 662-792) --
  * Renders global sample indices [spp_begin, spp_begin+spp_count) of every pixel.  `out_rgb` is W*H*3 fp32 in the

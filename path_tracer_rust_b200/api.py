@@ -67,7 +67,7 @@ _lib_lock = threading.Lock()
 
 # every symbol include/ptb.h declares
 ABI_SYMBOLS = ["ptb_scene_load_json", "ptb_scene_get_desc", "ptb_scene_id", "ptb_scene_free", "ptb_abi_version",
-               "ptb_device_count", "ptb_create", "ptb_destroy", "ptb_last_error", "ptb_upload_scene", "ptb_get_stats",
+               "ptb_device_count", "ptb_create", "ptb_destroy", "ptb_last_error", "ptb_upload_scene", "ptb_get_stats", "ptb_set_option",
                "ptb_render", "ptb_render_device", "ptb_resolve_device", "ptb_primary_hits", "ptb_intersect",
                "ptb_to_int_with_gamma_correction", "ptb_write_ppm", "ptb_hash_pixels"]
 
@@ -96,6 +96,7 @@ def load_library():
         L.ptb_last_error.argtypes = [C.c_void_p]
         L.ptb_upload_scene.argtypes = [C.c_void_p, C.POINTER(_SceneDesc)]
         L.ptb_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        L.ptb_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
         L.ptb_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, fp,
                                  C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]
         L.ptb_render_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p,
@@ -276,6 +277,9 @@ class Backend:
     def upload_scene(self, scene: Scene):
         self._check(self.L.ptb_upload_scene(self._h, scene._desc))
         self._scene = scene
+
+    def set_option(self, key: str, value: float):
+        self._check(self.L.ptb_set_option(self._h, key.encode(), float(value)))
 
     def stats(self) -> dict:
         s = Stats()

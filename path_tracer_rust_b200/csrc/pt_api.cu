@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../include/ptb.h"
+#include "pt_bvh.cuh"
 #include "pt_bvh_build.h"
 #include "pt_launch.h"
 #include "scene_io.hpp"
@@ -68,6 +69,7 @@ struct ptb_ctx {
     DScene ds{};
     DevBuf<float4> loose_obj, loose_tri, obj_gate, mat_color, mat_emis;
     BvhDevice bvh;
+    BvhOptions bvh_opt;
     DevBuf<float> fb, scratch_f;
     DevBuf<int> scratch_i;
     DevBuf<int> tile_counter;
@@ -255,7 +257,7 @@ extern "C" int ptb_upload_scene(ptb_ctx *ctx, const ptb_scene_desc *desc) {
 
     // split: which objects go to the BVH, which stay in the lock-step shared-memory list
     std::vector<char> in_bvh(nobj, 0);
-    choose_bvh_objects(*desc, ctx->max_smem_optin, in_bvh);
+    choose_bvh_objects(*desc, ctx->max_smem_optin, ctx->bvh_opt, in_bvh);
 
     std::vector<float4> lobj, ltri;
     for (size_t k = nobj; k-- > 0;) {  // reverse index order = the reference's scan order
@@ -296,7 +298,7 @@ extern "C" int ptb_upload_scene(ptb_ctx *ctx, const ptb_scene_desc *desc) {
     ds.n_loose_obj = static_cast<int>(lobj.size() / 2); ds.n_loose_tri = static_cast<int>(ltri.size() / 3);
     ds.obj_gate = ctx->obj_gate.p; ds.mat_color = ctx->mat_color.p; ds.mat_emis = ctx->mat_emis.p;
     ds.n_obj = static_cast<int>(nobj);
-    ds.bvh_root = BVH_EMPTY;
+    ds.bvh_root = BVH_EMPTY_REF;
 
     // camera frame, once per scene like render() (mod.rs:998-999; CameraData mod.rs:211-232)
     {
@@ -328,6 +330,15 @@ extern "C" int ptb_upload_scene(ptb_ctx *ctx, const ptb_scene_desc *desc) {
     ctx->stats.n_loose_objects = static_cast<uint32_t>(ds.n_loose_obj);
     ctx->stats.n_loose_triangles = static_cast<uint32_t>(ds.n_loose_tri);
     ctx->has_scene = true;
+    return PTB_OK;
+}
+
+extern "C" int ptb_set_option(ptb_ctx *ctx, const char *key, double value) {
+    if (!ctx || !key) return fail(ctx, PTB_ERR_ARG, "ptb_set_option: null argument");
+    const std::string k = key;
+    if (k == "bvh_min_tris") ctx->bvh_opt.min_tris = value;
+    else if (k == "bvh_min_spheres") ctx->bvh_opt.min_spheres = value;
+    else return fail(ctx, PTB_ERR_ARG, "ptb_set_option: unknown key " + k);
     return PTB_OK;
 }
 

@@ -1,26 +1,435 @@
-// pt_bvh_build.cu -- device BVH construction (stub: everything stays in the shared-memory list)
+// pt_bvh_build.cu -- LBVH construction on the device (Karras 2012): Morton codes -> radix sort (CUB) -> hierarchy ->
+// bottom-up refit -> collapse small subtrees into multi-primitive leaves -> 64-byte two-child nodes.
+//
+// New with respect to the reference (which is brute force, src/render/mod.rs:631-659 / :554-615).  The hierarchy only
+// selects which primitives are tested; the tests themselves are the reference's arithmetic (pt_device.cuh), and the
+// boxes are padded so no hit the reference's fp32 test would accept can be culled (triangle_pad / sphere_extent below).
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "pt_bvh.cuh"
 #include "pt_bvh_build.h"
 #include "pt_launch.h"
 
 namespace ptb {
 
-void choose_bvh_objects(const ptb_scene_desc &desc, size_t, std::vector<char> &in_bvh) {
-    in_bvh.assign(desc.n_objects, 0);
+namespace {
+
+constexpr int LEAF_MAX = 4;          // primitives per leaf after collapsing (<= 8 by the leaf encoding)
+constexpr float UNIT_ROUNDOFF = 5.9604645e-8f;  // 2^-24
+
+inline float4 f4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+inline float ibits(int32_t v) { float f; std::memcpy(&f, &v, 4); return f; }
+inline float ubits(uint32_t v) { float f; std::memcpy(&f, &v, 4); return f; }
+inline V3 v3(const float *p) { return mk3(p[0], p[1], p[2]); }
+
+// How far (in world units) the point o + d*t_c of a hit ACCEPTED by the reference's fp32 Moeller-Trumbore test
+// (mod.rs:560-593) can lie from the true triangle.  First-order forward error analysis with unit roundoff u:
+//   |d det| <= 7u|e1||e2|,  |d(tv.p)| <= 8u|tv||e2|,  |d(d.q)| <= 8u|tv||e1|,  |d(e2.q)| <= 8u|tv||e1||e2|,
+// the accepted |det| is >= 1e-4 (mod.rs:571), |tv| and t are bounded by D (distance bound between any ray origin and
+// the scene), so  |du||e1| + |dv||e2| + |dt|  <=  u |e1||e2| (31 D + 7 L) / 1e-4 + 2u (L + D),  L = |e1| + |e2|.
+// A safety factor 2 covers the second-order terms; the last term covers the slab test's own fp32 rounding.
+inline float triangle_pad(V3 e1, V3 e2, float D, float coord_max) {
+    const double l1 = std::sqrt((double)e1.x * e1.x + (double)e1.y * e1.y + (double)e1.z * e1.z);
+    const double l2 = std::sqrt((double)e2.x * e2.x + (double)e2.y * e2.y + (double)e2.z * e2.z);
+    const double u = UNIT_ROUNDOFF, L = l1 + l2;
+    const double grazing = u * l1 * l2 * (31.0 * D + 7.0 * L) / 1e-4;
+    const double pad = 2.0 * (grazing + 2.0 * u * (L + D)) + 16.0 * u * (coord_max + D);
+    return (float)pad;
+}
+// Sphere (mod.rs:412-438): det = b^2 - |op|^2 + r^2 is accepted when >= 0; |d det| <= 12u|op|^2 + u r^2, and the
+// accepted point satisfies |P - c|^2 = r^2 + d det, so half extent = sqrt(r^2 + 2 * 13u D^2) (+ slab rounding).
+inline float sphere_extent(float r, float D, float coord_max) {
+    const double u = UNIT_ROUNDOFF;
+    return (float)(std::sqrt((double)r * r + 2.0 * 13.0 * u * ((double)D * D + (double)r * r)) + 16.0 * u * (coord_max + D));
 }
 
-cudaError_t bvh_build(const ptb_scene_desc &, const std::vector<char> &, const std::vector<uint32_t> &, BvhDevice &out, DScene &ds,
-                      cudaStream_t, double *build_ms, std::string &) {
-    out.n_nodes = out.n_tris = out.n_spheres = 0;
-    ds.bvh_root = BVH_EMPTY;
-    if (build_ms) *build_ms = 0.0;
-    return cudaSuccess;
+// ---------------------------------------------------------------------------------------------
+// device kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void k_prim_boxes(const float4 *__restrict__ recs, const float *__restrict__ pads, int n, float4 *__restrict__ blo,
+                             float4 *__restrict__ bhi) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 A = recs[3 * i], E1 = recs[3 * i + 1], E2 = recs[3 * i + 2];
+    const float p = pads[i];
+    float3 lo, hi;
+    if (__float_as_int(E1.w) < 0) {  // sphere: pads[] holds the half extent
+        lo = make_float3(A.x - p, A.y - p, A.z - p);
+        hi = make_float3(A.x + p, A.y + p, A.z + p);
+    } else {
+        const float bx = A.x + E1.x, by = A.y + E1.y, bz = A.z + E1.z;
+        const float cx = A.x + E2.x, cy = A.y + E2.y, cz = A.z + E2.z;
+        lo = make_float3(fminf(A.x, fminf(bx, cx)) - p, fminf(A.y, fminf(by, cy)) - p, fminf(A.z, fminf(bz, cz)) - p);
+        hi = make_float3(fmaxf(A.x, fmaxf(bx, cx)) + p, fmaxf(A.y, fmaxf(by, cy)) + p, fmaxf(A.z, fmaxf(bz, cz)) + p);
+    }
+    blo[i] = make_float4(lo.x, lo.y, lo.z, 0.f);
+    bhi[i] = make_float4(hi.x, hi.y, hi.z, 0.f);
+}
+
+__device__ __forceinline__ unsigned long long spread21(unsigned long long x) {  // 21 bits -> every third bit
+    x &= 0x1fffffull;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+
+__global__ void k_morton(const float4 *__restrict__ blo, const float4 *__restrict__ bhi, int n, float3 cmin, float3 cscale,
+                         unsigned long long *__restrict__ keys, int *__restrict__ idx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float cx = 0.5f * (blo[i].x + bhi[i].x), cy = 0.5f * (blo[i].y + bhi[i].y), cz = 0.5f * (blo[i].z + bhi[i].z);
+    const float fx = fminf(fmaxf((cx - cmin.x) * cscale.x, 0.f), 2097151.f);
+    const float fy = fminf(fmaxf((cy - cmin.y) * cscale.y, 0.f), 2097151.f);
+    const float fz = fminf(fmaxf((cz - cmin.z) * cscale.z, 0.f), 2097151.f);
+    keys[i] = spread21((unsigned long long)fx) << 2 | spread21((unsigned long long)fy) << 1 | spread21((unsigned long long)fz);
+    idx[i] = i;
+}
+
+__device__ __forceinline__ int delta(const unsigned long long *__restrict__ keys, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    const unsigned long long a = keys[i], b = keys[j];
+    if (a == b) return 64 + __clz(i ^ j);
+    return __clzll((long long)(a ^ b));
+}
+
+// one thread per internal node (Karras 2012, fig. 4); child ref >= 0: internal node, < 0: ~leaf index
+__global__ void k_hierarchy(const unsigned long long *__restrict__ keys, int n, int *__restrict__ left, int *__restrict__ right,
+                            int *__restrict__ first, int *__restrict__ last, int *__restrict__ parent_inner,
+                            int *__restrict__ parent_leaf) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    const int dmin = delta(keys, n, i, i - d);
+    int lmax = 2;
+    while (delta(keys, n, i, i + lmax * d) > dmin) lmax *= 2;
+    int l = 0;
+    for (int t = lmax / 2; t >= 1; t /= 2)
+        if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    const int j = i + l * d;
+    const int dnode = delta(keys, n, i, j);
+    int s = 0;
+    for (int t = (l + 1) / 2;; t = (t + 1) / 2) {
+        if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+        if (t <= 1) break;
+    }
+    const int gamma = i + s * d + min(d, 0);
+    const int lo = min(i, j), hi = max(i, j);
+    const int l_ref = (lo == gamma) ? ~gamma : gamma;
+    const int r_ref = (hi == gamma + 1) ? ~(gamma + 1) : gamma + 1;
+    left[i] = l_ref; right[i] = r_ref; first[i] = lo; last[i] = hi;
+    if (l_ref >= 0) parent_inner[l_ref] = i; else parent_leaf[~l_ref] = i;
+    if (r_ref >= 0) parent_inner[r_ref] = i; else parent_leaf[~r_ref] = i;
+    if (i == 0) parent_inner[0] = -1;
+}
+
+// bottom-up: the second thread to arrive at a node merges its children's boxes (children are complete by then)
+__global__ void k_refit(const int *__restrict__ idx, const float4 *__restrict__ blo, const float4 *__restrict__ bhi, int n,
+                        const int *__restrict__ left, const int *__restrict__ right, const int *__restrict__ parent_inner,
+                        const int *__restrict__ parent_leaf, int *__restrict__ flags, float4 *__restrict__ nlo,
+                        float4 *__restrict__ nhi, int *__restrict__ depth_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int node = parent_leaf[i];
+    int height = 1;
+    while (node >= 0) {
+        __threadfence();
+        if (atomicAdd(&flags[node], 1) == 0) return;
+        __threadfence();
+        const int l = left[node], r = right[node];
+        float4 alo, ahi, clo, chi;
+        if (l >= 0) { alo = __ldcg(&nlo[l]); ahi = __ldcg(&nhi[l]); } else { alo = blo[idx[~l]]; ahi = bhi[idx[~l]]; }
+        if (r >= 0) { clo = __ldcg(&nlo[r]); chi = __ldcg(&nhi[r]); } else { clo = blo[idx[~r]]; chi = bhi[idx[~r]]; }
+        // w carries the subtree height so the host can check it against the traversal stack
+        const float h = fmaxf(l >= 0 ? alo.w : 0.f, r >= 0 ? clo.w : 0.f) + 1.f;
+        __stcg(&nlo[node], make_float4(fminf(alo.x, clo.x), fminf(alo.y, clo.y), fminf(alo.z, clo.z), h));
+        __stcg(&nhi[node], make_float4(fmaxf(ahi.x, chi.x), fmaxf(ahi.y, chi.y), fmaxf(ahi.z, chi.z), 0.f));
+        height = (int)h;
+        node = parent_inner[node];
+    }
+    atomicMax(depth_out, height);
+}
+
+__global__ void k_alive(const int *__restrict__ first, const int *__restrict__ last, int n_inner, int *__restrict__ alive) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_inner) return;
+    alive[i] = (last[i] - first[i] + 1) > LEAF_MAX ? 1 : 0;
+}
+
+__device__ __forceinline__ void child_ref_and_box(int c, const int *alive, const int *new_index, const int *first, const int *last,
+                                                  const int *idx, const float4 *blo, const float4 *bhi, const float4 *nlo,
+                                                  const float4 *nhi, int &ref, float4 &lo, float4 &hi) {
+    if (c >= 0) {
+        lo = nlo[c]; hi = nhi[c];
+        if (alive[c]) ref = new_index[c];
+        else ref = ~((first[c] << 3) | (last[c] - first[c]));
+    } else {
+        const int k = ~c;
+        lo = blo[idx[k]]; hi = bhi[idx[k]];
+        ref = ~((k << 3) | 0);
+    }
+}
+
+__global__ void k_emit_nodes(int n_inner, const int *__restrict__ alive, const int *__restrict__ new_index,
+                             const int *__restrict__ left, const int *__restrict__ right, const int *__restrict__ first,
+                             const int *__restrict__ last, const int *__restrict__ idx, const float4 *__restrict__ blo,
+                             const float4 *__restrict__ bhi, const float4 *__restrict__ nlo, const float4 *__restrict__ nhi,
+                             float4 *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_inner || !alive[i]) return;
+    int r0, r1;
+    float4 l0, h0, l1, h1;
+    child_ref_and_box(left[i], alive, new_index, first, last, idx, blo, bhi, nlo, nhi, r0, l0, h0);
+    child_ref_and_box(right[i], alive, new_index, first, last, idx, blo, bhi, nlo, nhi, r1, l1, h1);
+    float4 *o = out + 4 * (size_t)new_index[i];
+    o[0] = make_float4(l0.x, l0.y, l0.z, h0.x);
+    o[1] = make_float4(h0.y, h0.z, l1.x, l1.y);
+    o[2] = make_float4(l1.z, h1.x, h1.y, h1.z);
+    o[3] = make_float4(__int_as_float(r0), __int_as_float(r1), 0.f, 0.f);
+}
+
+__global__ void k_gather_prims(const float4 *__restrict__ recs, const int *__restrict__ idx, int n, float4 *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int s = idx[i];
+    out[3 * i] = recs[3 * s]; out[3 * i + 1] = recs[3 * s + 1]; out[3 * i + 2] = recs[3 * s + 2];
+}
+
+template <typename T>
+cudaError_t dev_alloc(T **p, size_t n) { return cudaMalloc(reinterpret_cast<void **>(p), std::max<size_t>(n, 1) * sizeof(T)); }
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+void choose_bvh_objects(const ptb_scene_desc &desc, size_t max_smem_bytes, const BvhOptions &opt, std::vector<char> &in_bvh) {
+    const size_t n = desc.n_objects;
+    in_bvh.assign(n, 0);
+    uint64_t n_spheres = 0;
+    for (size_t k = 0; k < n; ++k) n_spheres += desc.objects[k].kind == PTB_OBJ_SPHERE;
+    for (size_t k = 0; k < n; ++k) {
+        const ptb_object &o = desc.objects[k];
+        if (o.kind == PTB_OBJ_MESH) in_bvh[k] = (double)o.tri_count >= opt.min_tris;
+        else in_bvh[k] = (double)n_spheres >= opt.min_spheres;
+    }
+    // the lock-step list must fit comfortably in shared memory (two CTAs per SM): move the largest meshes out first
+    auto loose_bytes = [&]() {
+        size_t b = 0;
+        for (size_t k = 0; k < n; ++k)
+            if (!in_bvh[k]) b += 32 + (desc.objects[k].kind == PTB_OBJ_MESH ? 48 * desc.objects[k].tri_count : 0);
+        return b;
+    };
+    const size_t budget = std::min<size_t>(max_smem_bytes, 96 * 1024);
+    while (loose_bytes() > budget) {
+        size_t big = n;
+        uint64_t big_n = 0;
+        for (size_t k = 0; k < n; ++k)
+            if (!in_bvh[k] && desc.objects[k].kind == PTB_OBJ_MESH && desc.objects[k].tri_count >= big_n) { big = k; big_n = desc.objects[k].tri_count; }
+        if (big == n || big_n == 0) {  // only spheres / empty meshes left: move all spheres
+            bool moved = false;
+            for (size_t k = 0; k < n; ++k)
+                if (!in_bvh[k] && desc.objects[k].kind == PTB_OBJ_SPHERE) { in_bvh[k] = 1; moved = true; }
+            if (!moved) break;
+        } else in_bvh[big] = 1;
+    }
 }
 
 void bvh_release(BvhDevice &b) {
     if (b.nodes) cudaFree(b.nodes);
     if (b.tris) cudaFree(b.tris);
-    if (b.spheres) cudaFree(b.spheres);
     b = BvhDevice{};
+}
+
+#define BV(expr)                                   \
+    do {                                           \
+        cudaError_t e__ = (expr);                  \
+        if (e__ != cudaSuccess) { err = #expr; rc = e__; goto done; } \
+    } while (0)
+
+cudaError_t bvh_build(const ptb_scene_desc &desc, const std::vector<char> &in_bvh, const std::vector<uint32_t> &prio_base,
+                      BvhDevice &out, DScene &ds, cudaStream_t st, double *build_ms, std::string &err) {
+    out.n_nodes = out.n_tris = out.n_spheres = 0;
+    out.max_depth = 0;
+    ds.bvh_root = BVH_EMPTY_REF;
+    ds.bvh_nodes = nullptr; ds.bvh_tri = nullptr; ds.bvh_sph = nullptr; ds.n_bvh_nodes = 0;
+    if (build_ms) *build_ms = 0.0;
+
+    // ---- host: distance bound D, primitive records, pads ----------------------------------------------------------------
+    // D bounds |o - a| and t for every ray the integrator can generate: origins are the lens centre or surface points.
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    auto grow = [&](double x, double y, double z, double r) {
+        const double p[3] = {x, y, z};
+        for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], p[k] - r); hi[k] = std::max(hi[k], p[k] + r); }
+    };
+    size_t n_prims = 0;
+    for (size_t k = 0; k < desc.n_objects; ++k) {
+        const ptb_object &o = desc.objects[k];
+        if (o.kind == PTB_OBJ_SPHERE) { grow(o.position[0], o.position[1], o.position[2], o.radius); n_prims += in_bvh[k] ? 1 : 0; }
+        else {
+            for (uint64_t j = 0; j < o.tri_count; ++j) {
+                const ptb_triangle &t = desc.triangles[o.tri_begin + j];
+                grow(t.a[0] + o.position[0], t.a[1] + o.position[1], t.a[2] + o.position[2], 0);
+                grow(t.b[0] + o.position[0], t.b[1] + o.position[1], t.b[2] + o.position[2], 0);
+                grow(t.c[0] + o.position[0], t.c[1] + o.position[1], t.c[2] + o.position[2], 0);
+            }
+            n_prims += in_bvh[k] ? o.tri_count : 0;
+        }
+    }
+    if (n_prims == 0) return cudaSuccess;
+    {
+        const ptb_camera &c = desc.camera;
+        grow(c.position[0] + c.direction[0] * c.focal_length, c.position[1] + c.direction[1] * c.focal_length,
+             c.position[2] + c.direction[2] * c.focal_length, 0);
+    }
+    const double diag = std::sqrt((hi[0] - lo[0]) * (hi[0] - lo[0]) + (hi[1] - lo[1]) * (hi[1] - lo[1]) + (hi[2] - lo[2]) * (hi[2] - lo[2]));
+    double coord_max = 0;
+    for (int k = 0; k < 3; ++k) coord_max = std::max(coord_max, std::max(std::fabs(lo[k]), std::fabs(hi[k])));
+    const float D = (float)(1.5 * diag);  // 1.5x: hit points are themselves computed with rounding and may sit just outside
+
+    std::vector<float4> recs;
+    std::vector<float> pads;
+    recs.reserve(3 * n_prims);
+    pads.reserve(n_prims);
+    unsigned n_tris = 0, n_sph = 0;
+    double cl[3] = {1e300, 1e300, 1e300}, ch[3] = {-1e300, -1e300, -1e300};
+    auto centroid = [&](double x, double y, double z) {
+        const double p[3] = {x, y, z};
+        for (int k = 0; k < 3; ++k) { cl[k] = std::min(cl[k], p[k]); ch[k] = std::max(ch[k], p[k]); }
+    };
+    for (size_t k = 0; k < desc.n_objects; ++k) {
+        if (!in_bvh[k]) continue;
+        const ptb_object &o = desc.objects[k];
+        if (o.kind == PTB_OBJ_SPHERE) {
+            recs.push_back(f4(o.position[0], o.position[1], o.position[2], ibits((int32_t)k)));
+            recs.push_back(f4(o.radius, 0.f, 0.f, ibits(-1)));
+            recs.push_back(f4(0.f, 0.f, 0.f, ubits(prio_base[k])));
+            pads.push_back(sphere_extent(o.radius, D, (float)coord_max));
+            centroid(o.position[0], o.position[1], o.position[2]);
+            n_sph++;
+        } else {
+            const V3 off = v3(o.position);
+            for (uint64_t j = 0; j < o.tri_count; ++j) {
+                const ptb_triangle &t = desc.triangles[o.tri_begin + j];
+                const V3 a = v3(t.a) + off, b = v3(t.b) + off, c = v3(t.c) + off;  // mod.rs:559
+                const V3 e1 = b - a, e2 = c - a;                                    // mod.rs:560-561
+                recs.push_back(f4(a.x, a.y, a.z, ibits((int32_t)k)));
+                recs.push_back(f4(e1.x, e1.y, e1.z, ibits((int32_t)j)));
+                recs.push_back(f4(e2.x, e2.y, e2.z, ubits(prio_base[k] + (uint32_t)j)));
+                pads.push_back(triangle_pad(e1, e2, D, (float)coord_max));
+                centroid(a.x + (e1.x + e2.x) / 3.0, a.y + (e1.y + e2.y) / 3.0, a.z + (e1.z + e2.z) / 3.0);
+                n_tris++;
+            }
+        }
+    }
+    const int n = (int)n_prims;
+
+    cudaError_t rc = cudaSuccess;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float4 *d_recs = nullptr, *d_blo = nullptr, *d_bhi = nullptr, *d_nlo = nullptr, *d_nhi = nullptr;
+    float *d_pads = nullptr;
+    unsigned long long *d_keys = nullptr, *d_keys2 = nullptr;
+    int *d_idx = nullptr, *d_idx2 = nullptr, *d_left = nullptr, *d_right = nullptr, *d_first = nullptr, *d_last = nullptr;
+    int *d_pin = nullptr, *d_pleaf = nullptr, *d_flags = nullptr, *d_alive = nullptr, *d_new = nullptr, *d_depth = nullptr;
+    void *d_tmp = nullptr;
+    size_t tmp_bytes = 0, tmp2 = 0;
+    const int T = 256, B = (n + T - 1) / T;
+    const int n_inner = n - 1;
+    int h_depth = 0, n_alive = 0;
+
+    BV(cudaEventCreate(&ev0)); BV(cudaEventCreate(&ev1));
+    BV(dev_alloc(&d_recs, 3 * (size_t)n)); BV(dev_alloc(&d_pads, (size_t)n));
+    BV(dev_alloc(&d_blo, (size_t)n)); BV(dev_alloc(&d_bhi, (size_t)n));
+    BV(dev_alloc(&d_keys, (size_t)n)); BV(dev_alloc(&d_keys2, (size_t)n));
+    BV(dev_alloc(&d_idx, (size_t)n)); BV(dev_alloc(&d_idx2, (size_t)n));
+    BV(dev_alloc(&d_left, (size_t)n)); BV(dev_alloc(&d_right, (size_t)n)); BV(dev_alloc(&d_first, (size_t)n)); BV(dev_alloc(&d_last, (size_t)n));
+    BV(dev_alloc(&d_pin, (size_t)n)); BV(dev_alloc(&d_pleaf, (size_t)n)); BV(dev_alloc(&d_flags, (size_t)n));
+    BV(dev_alloc(&d_alive, (size_t)n)); BV(dev_alloc(&d_new, (size_t)n)); BV(dev_alloc(&d_depth, 1));
+    BV(dev_alloc(&d_nlo, (size_t)n)); BV(dev_alloc(&d_nhi, (size_t)n));
+    BV(cudaMemcpyAsync(d_recs, recs.data(), recs.size() * sizeof(float4), cudaMemcpyHostToDevice, st));
+    BV(cudaMemcpyAsync(d_pads, pads.data(), pads.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    BV(cudaEventRecord(ev0, st));
+
+    // output arrays (kept): primitive records in leaf order
+    if (out.cap_tris < (size_t)n) {
+        if (out.tris) cudaFree(out.tris);
+        out.tris = nullptr; out.cap_tris = 0;
+        BV(dev_alloc(&out.tris, 3 * (size_t)n));
+        out.cap_tris = (size_t)n;
+    }
+
+    k_prim_boxes<<<B, T, 0, st>>>(d_recs, d_pads, n, d_blo, d_bhi);
+    BV(cudaGetLastError());
+    if (n > 1) {
+        float3 cmin = make_float3((float)cl[0], (float)cl[1], (float)cl[2]);
+        auto sc = [&](int k) { const double e = ch[k] - cl[k]; return (float)(e > 0 ? 2097151.0 / e : 0.0); };
+        float3 cscale = make_float3(sc(0), sc(1), sc(2));
+        k_morton<<<B, T, 0, st>>>(d_blo, d_bhi, n, cmin, cscale, d_keys, d_idx);
+        BV(cudaGetLastError());
+        BV(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys2, d_idx, d_idx2, n, 0, 63, st));
+        BV(cub::DeviceScan::ExclusiveSum(nullptr, tmp2, d_alive, d_new, n_inner, st));
+        tmp_bytes = std::max(tmp_bytes, tmp2);
+        BV(cudaMalloc(&d_tmp, std::max<size_t>(tmp_bytes, 16)));
+        BV(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys2, d_idx, d_idx2, n, 0, 63, st));
+        k_hierarchy<<<(n_inner + T - 1) / T, T, 0, st>>>(d_keys2, n, d_left, d_right, d_first, d_last, d_pin, d_pleaf);
+        BV(cudaGetLastError());
+        BV(cudaMemsetAsync(d_flags, 0, sizeof(int) * (size_t)n, st));
+        BV(cudaMemsetAsync(d_depth, 0, sizeof(int), st));
+        k_refit<<<B, T, 0, st>>>(d_idx2, d_blo, d_bhi, n, d_left, d_right, d_pin, d_pleaf, d_flags, d_nlo, d_nhi, d_depth);
+        BV(cudaGetLastError());
+        k_alive<<<(n_inner + T - 1) / T, T, 0, st>>>(d_first, d_last, n_inner, d_alive);
+        BV(cudaGetLastError());
+        BV(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_alive, d_new, n_inner, st));
+        int last_alive = 0, last_new = 0;
+        BV(cudaMemcpyAsync(&last_alive, d_alive + (n_inner - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+        BV(cudaMemcpyAsync(&last_new, d_new + (n_inner - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+        BV(cudaMemcpyAsync(&h_depth, d_depth, sizeof(int), cudaMemcpyDeviceToHost, st));
+        BV(cudaStreamSynchronize(st));
+        n_alive = last_alive + last_new;
+        if (h_depth > BVH_STACK) { err = "BVH deeper than the traversal stack"; rc = cudaErrorInvalidValue; goto done; }
+    } else {
+        BV(cudaMemcpyAsync(d_idx2, d_idx, 0, cudaMemcpyDeviceToDevice, st));
+        int zero = 0;
+        BV(cudaMemcpyAsync(d_idx2, &zero, sizeof(int), cudaMemcpyHostToDevice, st));
+    }
+    if (n_alive > 0) {
+        if (out.cap_nodes < (size_t)n_alive) {
+            if (out.nodes) cudaFree(out.nodes);
+            out.nodes = nullptr; out.cap_nodes = 0;
+            BV(dev_alloc(&out.nodes, 4 * (size_t)n_alive));
+            out.cap_nodes = (size_t)n_alive;
+        }
+        k_emit_nodes<<<(n_inner + T - 1) / T, T, 0, st>>>(n_inner, d_alive, d_new, d_left, d_right, d_first, d_last, d_idx2, d_blo,
+                                                           d_bhi, d_nlo, d_nhi, out.nodes);
+        BV(cudaGetLastError());
+        ds.bvh_root = 0;  // Karras' internal node 0 is the root and is always alive here
+    } else {
+        ds.bvh_root = ~((0 << 3) | (n - 1));  // the whole set fits one leaf
+    }
+    k_gather_prims<<<B, T, 0, st>>>(d_recs, d_idx2, n, out.tris);
+    BV(cudaGetLastError());
+    BV(cudaEventRecord(ev1, st));
+    BV(cudaStreamSynchronize(st));
+    {
+        float ms = 0.f;
+        BV(cudaEventElapsedTime(&ms, ev0, ev1));
+        if (build_ms) *build_ms = ms;
+    }
+    out.n_nodes = (unsigned)n_alive; out.n_tris = n_tris; out.n_spheres = n_sph; out.max_depth = h_depth;
+    ds.bvh_nodes = out.nodes; ds.bvh_tri = out.tris; ds.n_bvh_nodes = n_alive;
+
+done:
+    cudaFree(d_recs); cudaFree(d_pads); cudaFree(d_blo); cudaFree(d_bhi); cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_idx);
+    cudaFree(d_idx2); cudaFree(d_left); cudaFree(d_right); cudaFree(d_first); cudaFree(d_last); cudaFree(d_pin); cudaFree(d_pleaf);
+    cudaFree(d_flags); cudaFree(d_alive); cudaFree(d_new); cudaFree(d_depth); cudaFree(d_nlo); cudaFree(d_nhi); cudaFree(d_tmp);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (rc != cudaSuccess) ds.bvh_root = BVH_EMPTY_REF;
+    return rc;
 }
 
 }  // namespace ptb

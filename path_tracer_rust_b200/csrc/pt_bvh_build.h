@@ -12,15 +12,19 @@ namespace ptb {
 
 
 struct BvhDevice {
-    float4 *nodes = nullptr;
-    float4 *tris = nullptr;
-    float4 *spheres = nullptr;
+    float4 *nodes = nullptr;  // 4 x float4 per node
+    float4 *tris = nullptr;   // 3 x float4 per primitive (triangles and spheres), leaf order
     unsigned n_nodes = 0, n_tris = 0, n_spheres = 0;
-    size_t cap_nodes = 0, cap_tris = 0, cap_spheres = 0;
+    int max_depth = 0;
+    size_t cap_nodes = 0, cap_tris = 0;
 };
 
 // decides which objects are traversed through the BVH (in_bvh[k] = 1) and which stay in the shared-memory list
-void choose_bvh_objects(const ptb_scene_desc &desc, size_t max_smem_bytes, std::vector<char> &in_bvh);
+struct BvhOptions {
+    double min_tris = 24;     // meshes with fewer triangles stay in the lock-step shared-memory list
+    double min_spheres = 48;  // scenes with fewer spheres keep them in the shared-memory list
+};
+void choose_bvh_objects(const ptb_scene_desc &desc, size_t max_smem_bytes, const BvhOptions &opt, std::vector<char> &in_bvh);
 // builds the BVH over the chosen objects on the device and fills the bvh_* fields of `ds`
 cudaError_t bvh_build(const ptb_scene_desc &desc, const std::vector<char> &in_bvh, const std::vector<uint32_t> &prio_base,
                       BvhDevice &out, DScene &ds, cudaStream_t st, double *build_ms, std::string &err);

@@ -59,18 +59,19 @@ __device__ __forceinline__ void closest_hit_loose(const float4 *__restrict__ s_o
 __device__ __forceinline__ void finish_hit(const DScene &sc, const float4 *__restrict__ s_obj, const float4 *__restrict__ s_tri,
                                            const Hit &h, V3 o, V3 d, int &obj, int &tri, V3 &x, V3 &n) {
     x = o + d * h.t;  // mod.rs:430 / :604
-    if (h.ref & REF_SPHERE_BIT) {
-        const int i = h.ref & (REF_SPHERE_BIT - 1);
-        float4 sph, mb;
-        if (h.ref & REF_BVH_BIT) { sph = __ldg(&sc.bvh_sph[2 * i]); mb = __ldg(&sc.bvh_sph[2 * i + 1]); obj = __float_as_int(mb.x); }
-        else { sph = s_obj[2 * i]; mb = s_obj[2 * i + 1]; obj = __float_as_int(mb.w); }
+    const int k = h.ref & (REF_SPHERE_BIT - 1);
+    if (h.ref & REF_BVH_BIT) {
+        const float4 A = __ldg(&sc.bvh_tri[3 * k]), E1 = __ldg(&sc.bvh_tri[3 * k + 1]), E2 = __ldg(&sc.bvh_tri[3 * k + 2]);
+        obj = __float_as_int(A.w);
+        if (h.ref & REF_SPHERE_BIT) { tri = -1; n = normalize(x - xyz(A)); }
+        else { tri = __float_as_int(E1.w); n = normalize(cross(xyz(E1), xyz(E2))); }
+    } else if (h.ref & REF_SPHERE_BIT) {
+        const float4 sph = s_obj[2 * k], mb = s_obj[2 * k + 1];
+        obj = __float_as_int(mb.w);
         tri = -1;
         n = normalize(x - xyz(sph));  // mod.rs:431
     } else {
-        const int k = h.ref & (REF_SPHERE_BIT - 1);
-        float4 A, E1, E2;
-        if (h.ref & REF_BVH_BIT) { A = __ldg(&sc.bvh_tri[3 * k]); E1 = __ldg(&sc.bvh_tri[3 * k + 1]); E2 = __ldg(&sc.bvh_tri[3 * k + 2]); }
-        else { A = s_tri[3 * k]; E1 = s_tri[3 * k + 1]; E2 = s_tri[3 * k + 2]; }
+        const float4 A = s_tri[3 * k], E1 = s_tri[3 * k + 1], E2 = s_tri[3 * k + 2];
         obj = __float_as_int(A.w);
         tri = __float_as_int(E1.w);
         n = normalize(cross(xyz(E1), xyz(E2)));  // mod.rs:605
@@ -309,7 +310,7 @@ cudaError_t launch_intersect(const DScene &sc, const float *d_rays, unsigned lon
                              float *d_t, float *d_point, float *d_normal, int sm_count, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
     const size_t smem = loose_smem_bytes(sc);
-    const bool bvh = sc.bvh_root != BVH_EMPTY;
+    const bool bvh = sc.bvh_root != BVH_EMPTY_REF;
     auto kern = bvh ? k_intersect<true> : k_intersect<false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -322,7 +323,7 @@ cudaError_t launch_intersect(const DScene &sc, const float *d_rays, unsigned lon
 
 cudaError_t launch_render(const DScene &sc, const RenderArgs &a, int sm_count, cudaStream_t st) {
     const size_t smem = loose_smem_bytes(sc);
-    const bool bvh = sc.bvh_root != BVH_EMPTY;
+    const bool bvh = sc.bvh_root != BVH_EMPTY_REF;
     auto kern = bvh ? k_render<true> : k_render<false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

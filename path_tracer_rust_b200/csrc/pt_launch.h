@@ -10,7 +10,6 @@ namespace ptb {
 constexpr int TILE_W = 8, TILE_H = 4;  // one warp = one 8x4 pixel tile
 constexpr int RENDER_THREADS = 256;
 constexpr int RENDER_MIN_BLOCKS = 2;
-constexpr int BVH_EMPTY = -1;
 
 struct RenderArgs {
     int width, height;

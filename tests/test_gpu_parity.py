@@ -188,3 +188,79 @@ def test_render_mirror_of_reference_api(be):
     assert rgb.shape == (60, 90, 3)
     # ceiling light is at the top of the displayed image, floor at the bottom (SURVEY.md 8a orientation)
     assert rgb[:5].mean() > rgb[-5:].mean()
+
+
+# ---- BVH: same closest hit as the brute-force scan and as the oracle, bit for bit -------------------------------
+@pytest.fixture(scope="module")
+def synthetic_small(tmp_path_factory):
+    import importlib.util, os
+    from conftest import ROOT
+    spec = importlib.util.spec_from_file_location("mk", os.path.join(ROOT, "tools", "make_synthetic_scene.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    out = str(tmp_path_factory.mktemp("syn"))
+    return mk.make_synthetic(out, level=3, n_spheres=150, scale=4.0, seed=5), out
+
+
+def _cmp(a, b):
+    for x, y in zip(a, b):
+        assert np.array_equal(bits(x) if x.dtype == f32 else x, bits(y) if y.dtype == f32 else y)
+
+
+@pytest.mark.parametrize("which", ["mesh", "synthetic"])
+def test_bvh_equals_bruteforce_equals_oracle(which, synthetic_small):
+    import path_tracer_rust_b200 as P
+    import path_tracer_rust_b200.api as A
+    if which == "mesh":
+        path, base, ext = scene_path("mesh"), None, np.array([2.6, 2.0, 8.8], f32)
+    else:
+        path, base, ext = synthetic_small[0], synthetic_small[1], np.array([10.4, 8.0, 35.2], f32)
+    sc = P.Scene.load(path, base_dir=base)
+    osc = O.OracleScene(path, base)
+    bvh, bf = P.Backend(0), P.Backend(0)
+    try:
+        bf.set_option("bvh_min_tris", 1e18)
+        bf.set_option("bvh_min_spheres", 1e18)
+        bvh.upload_scene(sc)
+        bf.upload_scene(sc)
+        sb, sf = bvh.stats(), bf.stats()
+        assert sb["n_bvh_triangles"] > 0 and sb["n_bvh_nodes"] > 0
+        assert sf["n_bvh_triangles"] == 0 and sf["n_bvh_spheres"] == 0
+        if which == "synthetic":
+            assert sb["n_bvh_spheres"] == 150
+        rng = np.random.default_rng(77)
+        n = 300_000
+        o = (rng.uniform(-1, 1, (n, 3)) * ext).astype(f32)
+        d = rng.normal(size=(n, 3))
+        d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(f32)
+        # a third of the rays aim at the mesh so the BVH actually gets traversed deeply
+        centre = np.array([-0.8, -1.5, 0.0], f32) if which == "mesh" else np.array([0.0, -8.0 + 6.4 * 1.02, -4.0], f32)
+        tgt = centre + rng.normal(size=(n // 3, 3)).astype(f32) * f32(0.5 if which == "mesh" else 4.0)
+        dd = tgt - o[: n // 3]
+        d[: n // 3] = (dd / np.linalg.norm(dd, axis=1, keepdims=True)).astype(f32)
+        rays = np.concatenate([o, d], 1)
+        g_bvh, g_bf = bvh.intersect(rays), bf.intersect(rays)
+        _cmp(g_bvh, g_bf)
+        ref = osc.intersect(rays[:60_000])
+        _cmp([x[:60_000] for x in g_bvh], ref)
+        assert (g_bvh[1] >= 0).sum() > 1000              # plenty of triangle hits
+        # second generation from the hit points (self-intersection behaviour)
+        hit = g_bvh[0] >= 0
+        d2 = rng.normal(size=(int(hit.sum()), 3))
+        d2 = (d2 / np.linalg.norm(d2, axis=1, keepdims=True)).astype(f32)
+        rays2 = np.concatenate([g_bvh[3][hit], d2], 1)
+        _cmp(bvh.intersect(rays2), bf.intersect(rays2))
+        _cmp([x[:40_000] for x in bvh.intersect(rays2)], osc.intersect(rays2[:40_000]))
+        # primary rays and a lock-step image
+        W, H, spp = 120, 80, 4
+        _cmp(bvh.primary_hits(W, H), bf.primary_hits(W, H))
+        _cmp(bvh.primary_hits(W, H), osc.primary_hits(W, H))
+        a = bvh.render(W, H, spp, seed=3, out_kind=A.PTB_OUT_SUM)
+        seg_bvh = bvh.stats()["segments"]
+        b = bf.render(W, H, spp, seed=3, out_kind=A.PTB_OUT_SUM)
+        assert np.array_equal(bits(a), bits(b)) and seg_bvh == bf.stats()["segments"]
+        o_fb, o_st = osc.render_sum(W, H, spp, seed=3)
+        assert np.array_equal(bits(a), bits(o_fb)) and seg_bvh == int(o_st[0])
+    finally:
+        bvh.close()
+        bf.close()

@@ -106,6 +106,9 @@ int ptb_get_stats(const ptb_ctx *ctx, ptb_stats *out);
  *   "bvh_min_tris"    meshes with at least this many triangles are traversed through the BVH (default 24; a huge value = brute force)
  *   "bvh_min_spheres" scenes with at least this many spheres put them in the BVH (default 48) */
 int ptb_set_option(ptb_ctx *ctx, const char *key, double value);
+/* Device self-test: the kernels' own correctly-rounded reciprocal (MUFU.RCP + 2 FFMA, no range check) is compared with
+ * __frcp_rn over every float whose exponent field is in [1, 252]; *mismatches must come back 0. */
+int ptb_selftest(ptb_ctx *ctx, uint64_t *mismatches);
 
 /* ---- the hot path: replaces the rayon loop + render_pixel + radiance (mod.rs:1001-1024, 794-857, 662-792) --
  * Renders global sample indices [spp_begin, spp_begin+spp_count) of every pixel.  `out_rgb` is W*H*3 fp32 in the

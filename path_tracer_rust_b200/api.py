@@ -67,7 +67,7 @@ _lib_lock = threading.Lock()
 
 # every symbol include/ptb.h declares
 ABI_SYMBOLS = ["ptb_scene_load_json", "ptb_scene_get_desc", "ptb_scene_id", "ptb_scene_free", "ptb_abi_version",
-               "ptb_device_count", "ptb_create", "ptb_destroy", "ptb_last_error", "ptb_upload_scene", "ptb_get_stats", "ptb_set_option",
+               "ptb_device_count", "ptb_create", "ptb_destroy", "ptb_last_error", "ptb_upload_scene", "ptb_get_stats", "ptb_set_option", "ptb_selftest",
                "ptb_render", "ptb_render_device", "ptb_resolve_device", "ptb_primary_hits", "ptb_intersect",
                "ptb_to_int_with_gamma_correction", "ptb_write_ppm", "ptb_hash_pixels"]
 
@@ -97,6 +97,7 @@ def load_library():
         L.ptb_upload_scene.argtypes = [C.c_void_p, C.POINTER(_SceneDesc)]
         L.ptb_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         L.ptb_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+        L.ptb_selftest.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         L.ptb_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, fp,
                                  C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]
         L.ptb_render_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p,
@@ -280,6 +281,11 @@ class Backend:
 
     def set_option(self, key: str, value: float):
         self._check(self.L.ptb_set_option(self._h, key.encode(), float(value)))
+
+    def selftest(self) -> int:
+        bad = C.c_uint64(1)
+        self._check(self.L.ptb_selftest(self._h, C.byref(bad)))
+        return int(bad.value)
 
     def stats(self) -> dict:
         s = Stats()

@@ -248,7 +248,7 @@ extern "C" int ptb_upload_scene(ptb_ctx *ctx, const ptb_scene_desc *desc) {
         gate[i] = f4(0, 0, 0, 0);
         if (o.kind == PTB_OBJ_MESH) {
             const V3 c = v3(o.bs_position) + v3(o.position);  // mod.rs:268
-            gate[i] = f4(c.x, c.y, c.z, o.bs_radius);
+            gate[i] = f4(c.x, c.y, c.z, o.bs_radius * o.bs_radius);  // radius.powi(2), mod.rs:416
         }
         mcol[i] = f4(o.color[0], o.color[1], o.color[2], ibits(o.reflect_type));
         const bool emits = o.emission[0] != 0.0f || o.emission[1] != 0.0f || o.emission[2] != 0.0f;
@@ -264,7 +264,7 @@ extern "C" int ptb_upload_scene(ptb_ctx *ctx, const ptb_scene_desc *desc) {
         const ptb_object &o = desc->objects[k];
         if (in_bvh[k]) continue;
         if (o.kind == PTB_OBJ_SPHERE) {
-            lobj.push_back(f4(o.position[0], o.position[1], o.position[2], o.radius));
+            lobj.push_back(f4(o.position[0], o.position[1], o.position[2], o.radius * o.radius));
             lobj.push_back(f4(ibits(0), ubits(prio_base[k]), ibits(0), ibits(static_cast<int32_t>(k))));
         } else {
             lobj.push_back(gate[k]);
@@ -330,6 +330,18 @@ extern "C" int ptb_upload_scene(ptb_ctx *ctx, const ptb_scene_desc *desc) {
     ctx->stats.n_loose_objects = static_cast<uint32_t>(ds.n_loose_obj);
     ctx->stats.n_loose_triangles = static_cast<uint32_t>(ds.n_loose_tri);
     ctx->has_scene = true;
+    return PTB_OK;
+}
+
+extern "C" int ptb_selftest(ptb_ctx *ctx, uint64_t *mismatches) {
+    if (!ctx || !mismatches) return fail(ctx, PTB_ERR_ARG, "ptb_selftest: null argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemsetAsync(ctx->seg_counter.p, 0, sizeof(unsigned long long), ctx->stream));
+    CU(ctx, launch_rcp_selftest(ctx->seg_counter.p, ctx->sm_count, ctx->stream));
+    unsigned long long bad = 0;
+    CU(ctx, cudaMemcpyAsync(&bad, ctx->seg_counter.p, sizeof bad, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    *mismatches = bad;
     return PTB_OK;
 }
 

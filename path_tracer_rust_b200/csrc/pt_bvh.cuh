@@ -15,7 +15,7 @@
 //   n2 = (c1.lo.z, c1.hi.x, c1.hi.y, c1.hi.z)   n3 = (ref0, ref1, -, -) as int bits
 // ref >= 0: inner node index;  ref < 0: leaf, ~ref = (first_prim << 3) | (count - 1), prims contiguous in bvh_tri.
 // Primitive record = 3 x float4 (same as the shared-memory triangle record); a sphere is stored as
-//   (centre | obj), (radius, 0, 0 | -1), (0, 0, 0 | prio).
+//   (centre | obj), (radius^2, 0, 0 | -1), (0, 0, 0 | prio).
 #pragma once
 #include "pt_device.cuh"
 
@@ -83,7 +83,7 @@ __device__ __forceinline__ void bvh_closest_hit(const DScene &sc, V3 o, V3 d, Hi
                         const int obj = __float_as_int(A.w);
                         if (obj != gate_obj) {
                             const float4 g = __ldg(&sc.obj_gate[obj]);
-                            gate_pass = sphere_t(xyz(g), g.w, o, d) >= 0.0f;
+                            gate_pass = sphere_gate(xyz(g), g.w, o, d);
                             gate_obj = obj;
                         }
                         ok = gate_pass;

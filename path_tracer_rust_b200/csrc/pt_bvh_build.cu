@@ -306,7 +306,7 @@ cudaError_t bvh_build(const ptb_scene_desc &desc, const std::vector<char> &in_bv
         const ptb_object &o = desc.objects[k];
         if (o.kind == PTB_OBJ_SPHERE) {
             recs.push_back(f4(o.position[0], o.position[1], o.position[2], ibits((int32_t)k)));
-            recs.push_back(f4(o.radius, 0.f, 0.f, ibits(-1)));
+            recs.push_back(f4(o.radius * o.radius, 0.f, 0.f, ibits(-1)));  // r^2 as in mod.rs:416
             recs.push_back(f4(0.f, 0.f, 0.f, ubits(prio_base[k])));
             pads.push_back(sphere_extent(o.radius, D, (float)coord_max));
             centroid(o.position[0], o.position[1], o.position[2]);

@@ -29,8 +29,8 @@ __device__ __forceinline__ void closest_hit_loose(const float4 *__restrict__ s_o
         const float4 sph = s_obj[2 * i];
         const float4 mb = s_obj[2 * i + 1];
         const int kind = __float_as_int(mb.x);
-        const float t = sphere_t(xyz(sph), sph.w, o, d);
         if (kind == KIND_SPHERE) {
+            const float t = sphere_t(xyz(sph), sph.w, o, d);
             if (t >= 0.0f && t < best.t) {
                 best.t = t;
                 best.prio = (uint32_t)__float_as_int(mb.y);
@@ -38,7 +38,7 @@ __device__ __forceinline__ void closest_hit_loose(const float4 *__restrict__ s_o
             }
         } else {
             // mesh: bounding-sphere gate first (mod.rs:267-277); skip the triangle scan if no lane passes
-            const bool pass = t >= 0.0f;
+            const bool pass = sphere_gate(xyz(sph), sph.w, o, d);
             if (__any_sync(amask, pass)) {
                 const int k0 = __float_as_int(mb.y), k1 = k0 + __float_as_int(mb.z);
                 for (int k = k0; k < k1; ++k) {
@@ -169,30 +169,47 @@ __global__ void __launch_bounds__(RENDER_THREADS, RENDER_MIN_BLOCKS) k_render(co
         V3 acc = mk3(0.f, 0.f, 0.f);
         if (valid) acc = mk3(fb[0], fb[1], fb[2]);
 
-        unsigned long long s = a.spp_begin;
+        // Camera rays are generated in batches: every lane keeps one spare primary direction, a lane that finishes a path
+        // just swaps it in, and the (long, otherwise badly diverged) ray-generation code runs only when REGEN_BATCH lanes
+        // need a new spare or some lane would have to idle.  Per-lane order of samples and of `acc += L` is unchanged.
+        unsigned long long s_next = a.spp_begin, s = a.spp_begin;
         const unsigned long long s_end = a.spp_begin + a.spp_count;
-        bool active = valid && s < s_end;
-        bool need_new = true;
+        bool has_path = false, spare_ok = false;
+        V3 spare_d = mk3(0.f, 0.f, 1.f);
         V3 o = mk3(0.f, 0.f, 0.f), d = mk3(0.f, 0.f, 1.f), T = mk3(1.f, 1.f, 1.f), L = mk3(0.f, 0.f, 0.f);
         int depth = 0, sp = 0;
         uint32_t event = 0, nseg = 0;
         PathStackEntry stk[2];
 
         for (;;) {
-            const unsigned amask = __ballot_sync(0xffffffffu, active);
-            if (amask == 0u) break;
-            if (active) {
-                uint32_t rnd[4];
-                if (need_new) {  // camera sample: event 0, slots 0,1 (mod.rs:814-843)
-                    philox4x32_10(pixel, (uint32_t)s, (uint32_t)(s >> 32), 0u, k0, k1, rnd);
-                    const float ysub = (float)((s / 2) % 2), xsub = (float)(s % 2);
+            const bool need = valid && !spare_ok && s_next < s_end;
+            const unsigned need_mask = __ballot_sync(0xffffffffu, need);
+            const bool starving = __any_sync(0xffffffffu, need && !has_path);
+            if (starving || __popc(need_mask) >= REGEN_BATCH) {
+                if (need) {  // camera sample: event 0, slots 0,1 (mod.rs:814-843)
+                    uint32_t rnd[4];
+                    philox4x32_10(pixel, (uint32_t)s_next, (uint32_t)(s_next >> 32), 0u, k0, k1, rnd);
+                    const float ysub = (float)((s_next / 2) % 2), xsub = (float)(s_next % 2);
                     const float r1 = 2.0f * u32_to_unit(rnd[0]);
                     const float r2 = 2.0f * u32_to_unit(rnd[1]);
-                    camera_ray(sc, W, H, px, y, xsub, ysub, tent(r1), tent(r2), o, d);
-                    T = mk3(1.f, 1.f, 1.f); L = mk3(0.f, 0.f, 0.f);
-                    depth = 0; sp = 0; event = 0;
-                    need_new = false;
+                    V3 o_unused;
+                    camera_ray(sc, W, H, px, y, xsub, ysub, tent(r1), tent(r2), o_unused, spare_d);
+                    spare_ok = true;
+                    s_next++;
                 }
+            }
+            if (!has_path && spare_ok) {  // start sample s = s_next - 1
+                o = sc.lens_center; d = spare_d;
+                T = mk3(1.f, 1.f, 1.f); L = mk3(0.f, 0.f, 0.f);
+                depth = 0; sp = 0; event = 0;
+                s = s_next - 1;
+                spare_ok = false;
+                has_path = true;
+            }
+            const unsigned amask = __ballot_sync(0xffffffffu, has_path);
+            if (amask == 0u) break;
+            if (has_path) {
+                uint32_t rnd[4];
                 // ---- one radiance() call (mod.rs:662): event k, slots 0 = RR, 1,2 = diffuse, 3 = refraction choice
                 event++;
                 nseg++;
@@ -270,8 +287,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, RENDER_MIN_BLOCKS) k_render(co
                         o = stk[sp].o; d = stk[sp].d; T = stk[sp].T; depth = stk[sp].depth;
                     } else {  // sample finished: radiance_v += radiance (mod.rs:846)
                         acc = acc + L;
-                        s++;
-                        if (s < s_end) need_new = true; else active = false;
+                        has_path = false;
                     }
                 }
             }
@@ -293,6 +309,19 @@ __global__ void k_resolve(const float *__restrict__ sum, unsigned long long n, f
     }
 }
 
+// exhaustive check of rcp_rn_normal against __frcp_rn over every float whose exponent field is in [1, 252]
+__global__ void k_rcp_selftest(unsigned long long *mismatches) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned long long bad = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < (1ull << 32); i += stride) {
+        const uint32_t bits = (uint32_t)i, e = (bits >> 23) & 0xffu;
+        if (e < 1u || e > 252u) continue;
+        const float x = __uint_as_float(bits);
+        if (__float_as_uint(rcp_rn_normal(x)) != __float_as_uint(__frcp_rn(x))) bad++;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 // a*b+c with operands chosen so that a fused multiply-add gives a different answer
 __global__ void k_contraction_probe(float a, float b, float c, float *out) { out[0] = a * b + c; }
 
@@ -300,6 +329,11 @@ __global__ void k_contraction_probe(float a, float b, float c, float *out) { out
 // host launchers
 // ---------------------------------------------------------------------------------------------
 static size_t loose_smem_bytes(const DScene &sc) { return sizeof(float4) * (2ull * sc.n_loose_obj + 3ull * sc.n_loose_tri); }
+
+cudaError_t launch_rcp_selftest(unsigned long long *d_mismatches, int sm_count, cudaStream_t st) {
+    k_rcp_selftest<<<sm_count * 8, 256, 0, st>>>(d_mismatches);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_contraction_probe(float a, float b, float c, float *d_out, cudaStream_t st) {
     k_contraction_probe<<<1, 1, 0, st>>>(a, b, c, d_out);

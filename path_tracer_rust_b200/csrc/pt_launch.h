@@ -9,7 +9,8 @@ namespace ptb {
 
 constexpr int TILE_W = 8, TILE_H = 4;  // one warp = one 8x4 pixel tile
 constexpr int RENDER_THREADS = 256;
-constexpr int RENDER_MIN_BLOCKS = 2;
+constexpr int RENDER_MIN_BLOCKS = 3;
+constexpr int REGEN_BATCH = 12;        // lanes that must be waiting for a camera ray before the ray-gen code runs
 
 struct RenderArgs {
     int width, height;
@@ -21,6 +22,7 @@ struct RenderArgs {
     unsigned long long *segment_counter;   // += closest-hit queries
 };
 
+cudaError_t launch_rcp_selftest(unsigned long long *d_mismatches, int sm_count, cudaStream_t st);
 cudaError_t launch_contraction_probe(float a, float b, float c, float *d_out, cudaStream_t st);
 cudaError_t launch_intersect(const DScene &sc, const float *d_rays, unsigned long long n, int pw, int ph, int *d_obj, int *d_tri,
                              float *d_t, float *d_point, float *d_normal, int sm_count, cudaStream_t st);

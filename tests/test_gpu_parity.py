@@ -32,6 +32,11 @@ def bits(a):
     return np.ascontiguousarray(a, f32).view(np.uint32)
 
 
+def test_device_reciprocal_is_correctly_rounded(be):
+    """rcp_rn_normal (used in Moeller-Trumbore) == __frcp_rn for every float with exponent field in [1, 252]"""
+    assert be.selftest() == 0
+
+
 # ---- known answers of the reference's own tests, through the CUDA kernels (test.rs:43-144) ------------------
 def test_reference_sphere_kats_on_gpu(be, kat_scene):
     load_both(be, kat_scene([sphere_obj((0, 0, -3))], "k1"))

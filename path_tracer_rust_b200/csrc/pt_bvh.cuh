@@ -42,17 +42,30 @@ __device__ __forceinline__ bool slab(float lx, float ly, float lz, float hx, flo
     return tn <= tf;
 }
 
+// While-while traversal (Aila & Laine 2009): every lane first descends through inner nodes until it holds a leaf (or is
+// done), then all lanes that hold a leaf test its primitives together; the leaf code, which is the longest, then runs
+// with many lanes instead of one or two.  The stack stores the entry distance of a postponed child so that it can be
+// dropped at pop time once a closer hit is known (strictly farther only: ties must still be visited for the prio rule).
 __device__ __forceinline__ void bvh_closest_hit(const DScene &sc, V3 o, V3 d, Hit &best) {
     int cur = sc.bvh_root;
     if (cur == BVH_EMPTY_REF) return;
     const V3 id = mk3(safe_rcp_dir(d.x), safe_rcp_dir(d.y), safe_rcp_dir(d.z));
     const V3 ood = mk3(o.x * id.x, o.y * id.y, o.z * id.z);
-    int stack[BVH_STACK];
+    int stack_ref[BVH_STACK];
+    float stack_t[BVH_STACK];
     int sp = 0;
     int gate_obj = -1;
     bool gate_pass = false;
-    for (;;) {
-        if (cur >= 0) {
+#define PTB_BVH_POP()                                                    \
+    do {                                                                 \
+        cur = BVH_EMPTY_REF;                                             \
+        while (sp > 0) {                                                 \
+            --sp;                                                        \
+            if (stack_t[sp] <= best.t) { cur = stack_ref[sp]; break; }   \
+        }                                                                \
+    } while (0)
+    while (cur != BVH_EMPTY_REF) {
+        while (cur >= 0) {
             const float4 *n = sc.bvh_nodes + 4 * (size_t)cur;
             const float4 n0 = __ldg(n), n1 = __ldg(n + 1), n2 = __ldg(n + 2), n3 = __ldg(n + 3);
             float t0, t1;
@@ -62,12 +75,14 @@ __device__ __forceinline__ void bvh_closest_hit(const DScene &sc, V3 o, V3 d, Hi
             if (h0 && h1) {
                 const bool first0 = t0 <= t1;
                 cur = first0 ? r0 : r1;
-                if (sp < BVH_STACK) stack[sp++] = first0 ? r1 : r0;
-                continue;
-            }
-            if (h0) { cur = r0; continue; }
-            if (h1) { cur = r1; continue; }
-        } else {
+                stack_ref[sp] = first0 ? r1 : r0;
+                stack_t[sp] = first0 ? t1 : t0;
+                sp++;
+            } else if (h0) cur = r0;
+            else if (h1) cur = r1;
+            else PTB_BVH_POP();
+        }
+        if (cur != BVH_EMPTY_REF) {
             const int code = ~cur;
             const int first = code >> 3, count = (code & 7) + 1;
             for (int k = first; k < first + count; ++k) {
@@ -95,10 +110,10 @@ __device__ __forceinline__ void bvh_closest_hit(const DScene &sc, V3 o, V3 d, Hi
                     }
                 }
             }
+            PTB_BVH_POP();
         }
-        if (sp == 0) break;
-        cur = stack[--sp];
     }
+#undef PTB_BVH_POP
 }
 
 }  // namespace ptb

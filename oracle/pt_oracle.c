@@ -27,14 +27,19 @@
  *
  * Modes that are NOT in the reference but are needed to compare against a GPU:
  *   - RNG "philox": counter based Philox4x32-10, key = seed, counter = (pixel, sample_lo,
- *     sample_hi, event); event 0 is the camera sample (slots 0,1 = r1,r2), event k>=1 is the k-th
- *     radiance() call of the sample in depth-first order (slot 0 = Russian roulette, 1,2 = diffuse
- *     r1,r2, 3 = refraction choice).  The reference draws from an OS-seeded thread-local ChaCha12
- *     (mod.rs:53) and is not reproducible, so only the distribution can be matched.
+ *     sample_hi, event); event 0 is the camera sample (slots 0,1 = r1,r2); the radiance() call at
+ *     depth new_depth (1..12) of path-tree branch `code` has event (code << 4) | new_depth, where
+ *     code (0..3) says which of the two deterministic refraction splits (mod.rs:775-786, depth 1
+ *     and 2) were left through the transmitted child (bit 0 / bit 1).  Slot 0 = Russian roulette,
+ *     1,2 = diffuse r1,r2, 3 = refraction choice.  Events are therefore independent of evaluation
+ *     order, which lets a wavefront GPU integrator trace both children of a split concurrently.
+ *     The reference draws from an OS-seeded thread-local ChaCha12 (mod.rs:53) and is not
+ *     reproducible, so only the distribution can be matched.
  *   - "det" sin/cos: a fixed fp32 polynomial (Cephes sinf/cosf form) evaluated with un-fused ops so
  *     CPU and GPU agree bit for bit; "libm" is the reference's behaviour (f32::sin/cos -> sinf/cosf).
  *   - "forward" accumulation: iterative throughput form of radiance() with a 2-entry stack, the
- *     bit-exact twin of the CUDA integrator.  "recursive" is the reference's form.
+ *     bit-exact twin of the CUDA integrators.  Every branch of the path tree (code 0..3) sums its own
+ *     emission terms; the sample's radiance is ((L0 + L1) + L2) + L3.  "recursive" is the reference's form.
  */
 #define _GNU_SOURCE
 #include <ctype.h>
@@ -330,10 +335,10 @@ static int refract_terms(v3 d, v3 n, v3 nl, fresnel_t *f) {
 /* radiance  mod.rs:661-792  (reference form: recursive)                                         */
 /* ------------------------------------------------------------------------------------------ */
 #define MAX_DEPTH 12
-static v3 radiance_rec(const ray_t *ray, int depth, sampler_t *S) {
+static v3 radiance_rec(const ray_t *ray, int depth, int code, sampler_t *S) {
     hit_t hit;
     S->n_segments++;
-    sampler_event(S, S->event + 1);
+    sampler_event(S, ((uint32_t)code << 4) | (uint32_t)(depth + 1));
     int id = intersect_scene(S->sc, ray, &hit, S);
     if (id < 0) return V(0.0f, 0.0f, 0.0f);
     const obj_t *o = &S->sc->objs[id];
@@ -349,25 +354,25 @@ static v3 radiance_rec(const ray_t *ray, int depth, sampler_t *S) {
     switch (o->refl) {
     case REFL_DIFFUSE: {
         ray_t r = {hit.x, diffuse_dir(S, nl)};
-        inner = v_mul(color, radiance_rec(&r, new_depth, S));
+        inner = v_mul(color, radiance_rec(&r, new_depth, code, S));
     } break;
     case REFL_SPECULAR: {
         ray_t r = {hit.x, reflect_dir(ray->d, hit.n)};
-        inner = v_mul(color, radiance_rec(&r, new_depth, S));
+        inner = v_mul(color, radiance_rec(&r, new_depth, code, S));
     } break;
     default: {
         ray_t refl = {hit.x, reflect_dir(ray->d, hit.n)};
         fresnel_t f;
         if (!refract_terms(ray->d, hit.n, nl, &f)) {
-            inner = v_mul(color, radiance_rec(&refl, new_depth, S));
+            inner = v_mul(color, radiance_rec(&refl, new_depth, code, S));
         } else {
             ray_t tr = {hit.x, f.tdir};
             if (new_depth > 2) {
-                if (rand01(S, 3) < f.p) inner = v_scale(v_mul(color, radiance_rec(&refl, new_depth, S)), f.rp);
-                else inner = v_scale(v_mul(color, radiance_rec(&tr, new_depth, S)), f.tp);
+                if (rand01(S, 3) < f.p) inner = v_scale(v_mul(color, radiance_rec(&refl, new_depth, code, S)), f.rp);
+                else inner = v_scale(v_mul(color, radiance_rec(&tr, new_depth, code, S)), f.tp);
             } else { /* mod.rs:776-785: reflection child evaluated first */
-                v3 a = v_scale(radiance_rec(&refl, new_depth, S), f.re);
-                v3 b = v_scale(radiance_rec(&tr, new_depth, S), f.tr);
+                v3 a = v_scale(radiance_rec(&refl, new_depth, code, S), f.re);
+                v3 b = v_scale(radiance_rec(&tr, new_depth, code | (1 << (new_depth - 1)), S), f.tr);
                 inner = v_mul(color, v_add(a, b));
             }
         }
@@ -379,15 +384,16 @@ static v3 radiance_rec(const ray_t *ray, int depth, sampler_t *S) {
 /* forward (throughput) form: bit-exact twin of the CUDA integrator; same paths, same draws,
  * different association of the colour products (differs from radiance_rec by rounding only). */
 static v3 radiance_fwd(const ray_t *ray0, sampler_t *S) {
-    struct { ray_t r; v3 T; int depth; } stack[2];
+    struct { ray_t r; v3 T; int depth, code; } stack[2];
     int sp = 0;
-    v3 L = V(0.0f, 0.0f, 0.0f), T = V(1.0f, 1.0f, 1.0f);
+    v3 Lc[4] = {{0.0f, 0.0f, 0.0f}, {0.0f, 0.0f, 0.0f}, {0.0f, 0.0f, 0.0f}, {0.0f, 0.0f, 0.0f}};
+    v3 T = V(1.0f, 1.0f, 1.0f);
     ray_t ray = *ray0;
-    int depth = 0;
+    int depth = 0, code = 0;
     for (;;) {
         hit_t hit;
         S->n_segments++;
-        sampler_event(S, S->event + 1);
+        sampler_event(S, ((uint32_t)code << 4) | (uint32_t)(depth + 1));
         int id = intersect_scene(S->sc, &ray, &hit, S);
         if (id >= 0) {
             const obj_t *o = &S->sc->objs[id];
@@ -400,7 +406,7 @@ static v3 radiance_fwd(const ray_t *ray0, sampler_t *S) {
                 if (rand01(S, 0) < max_reflection && new_depth < MAX_DEPTH) color = v_scale(color, 1.0f / max_reflection);
                 else alive = 0;
             }
-            L = v_add(L, v_mul(T, o->emission));
+            Lc[code] = v_add(Lc[code], v_mul(T, o->emission));
             if (alive) {
                 v3 Tc = v_mul(T, color);
                 if (o->refl == REFL_DIFFUSE) {
@@ -419,7 +425,8 @@ static v3 radiance_fwd(const ray_t *ray0, sampler_t *S) {
                         else { T = v_scale(Tc, f.tp); ray.d = f.tdir; }
                     } else {
                         stack[sp].r.o = hit.x; stack[sp].r.d = f.tdir;
-                        stack[sp].T = v_scale(Tc, f.tr); stack[sp].depth = new_depth; sp++;
+                        stack[sp].T = v_scale(Tc, f.tr); stack[sp].depth = new_depth;
+                        stack[sp].code = code | (1 << (new_depth - 1)); sp++;
                         T = v_scale(Tc, f.re); ray.d = rd;
                     }
                     ray.o = hit.x; depth = new_depth;
@@ -427,9 +434,10 @@ static v3 radiance_fwd(const ray_t *ray0, sampler_t *S) {
                 }
             }
         }
-        if (sp == 0) return L;
-        sp--; ray = stack[sp].r; T = stack[sp].T; depth = stack[sp].depth;
+        if (sp == 0) break;
+        sp--; ray = stack[sp].r; T = stack[sp].T; depth = stack[sp].depth; code = stack[sp].code;
     }
+    return v_add(v_add(v_add(Lc[0], Lc[1]), Lc[2]), Lc[3]);
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -465,6 +473,7 @@ static inline float tent(float r) { /* mod.rs:820-830 */
 /* render_pixel  mod.rs:794-857, without the final /spp and clamp (see pto_resolve) */
 static v3 render_pixel_sum(const struct pto_scene *sc, const cam_frame_t *cf, int W, int H, uint32_t pixel_index,
                            uint64_t spp_begin, uint64_t spp_count, v3 acc, const pto_render_cfg *cfg, sampler_t *S) {
+    (void)sc;
     int y = H - 1 - (int)(pixel_index / (uint32_t)W);
     int x = (int)(pixel_index % (uint32_t)W);
     sampler_seed_pixel(S, cfg->seed, pixel_index);
@@ -476,7 +485,7 @@ static v3 render_pixel_sum(const struct pto_scene *sc, const cam_frame_t *cf, in
         float r1 = 2.0f * rand01(S, 0);
         float r2 = 2.0f * rand01(S, 1);
         ray_t ray = camera_ray(cf, W, H, x, y, xsub, ysub, tent(r1), tent(r2));
-        v3 rad = cfg->accum_mode == PTO_ACCUM_FORWARD ? radiance_fwd(&ray, S) : radiance_rec(&ray, 0, S);
+        v3 rad = cfg->accum_mode == PTO_ACCUM_FORWARD ? radiance_fwd(&ray, S) : radiance_rec(&ray, 0, 0, S);
         acc = v_add(acc, rad);
     }
     return acc;
@@ -658,7 +667,7 @@ int pto_radiance_mean(const pto_scene *sc, const float *ray6, uint64_t n, const 
     for (uint64_t s = 0; s < n; ++s) {
         S.ctr_slo = (uint32_t)s; S.ctr_shi = (uint32_t)(s >> 32);
         S.event = 0;
-        v3 v = cfg->accum_mode == PTO_ACCUM_FORWARD ? radiance_fwd(&r, &S) : radiance_rec(&r, 0, &S);
+        v3 v = cfg->accum_mode == PTO_ACCUM_FORWARD ? radiance_fwd(&r, &S) : radiance_rec(&r, 0, 0, &S);
         acc[0] += v.x; acc[1] += v.y; acc[2] += v.z;
     }
     for (int i = 0; i < 3; ++i) mean3[i] = (float)(acc[i] / (double)n);

@@ -17,6 +17,7 @@
 #include "pt_bvh.cuh"
 #include "pt_bvh_build.h"
 #include "pt_launch.h"
+#include "pt_wavefront.h"
 #include "scene_io.hpp"
 
 using namespace ptb;
@@ -70,6 +71,9 @@ struct ptb_ctx {
     DevBuf<float4> loose_obj, loose_tri, obj_gate, mat_color, mat_emis;
     BvhDevice bvh;
     BvhOptions bvh_opt;
+    WfWorkspace wf;
+    int integrator = 0;             // 0 = auto (wavefront when the scene has a BVH), 1 = megakernel, 2 = wavefront
+    double wavefront_paths = 8388608.0;  // ray segments in flight per wavefront batch
     DevBuf<float> fb, scratch_f;
     DevBuf<int> scratch_i;
     DevBuf<int> tile_counter;
@@ -160,6 +164,7 @@ extern "C" void ptb_destroy(ptb_ctx *ctx) {
     ctx->mat_emis.release(); ctx->fb.release(); ctx->scratch_f.release(); ctx->scratch_i.release();
     ctx->tile_counter.release(); ctx->seg_counter.release();
     bvh_release(ctx->bvh);
+    wf_release(ctx->wf);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -350,6 +355,8 @@ extern "C" int ptb_set_option(ptb_ctx *ctx, const char *key, double value) {
     const std::string k = key;
     if (k == "bvh_min_tris") ctx->bvh_opt.min_tris = value;
     else if (k == "bvh_min_spheres") ctx->bvh_opt.min_spheres = value;
+    else if (k == "integrator") ctx->integrator = (int)value;
+    else if (k == "wavefront_paths") ctx->wavefront_paths = std::max(1024.0, value);
     else return fail(ctx, PTB_ERR_ARG, "ptb_set_option: unknown key " + k);
     return PTB_OK;
 }
@@ -408,9 +415,14 @@ extern "C" int ptb_render_device(ptb_ctx *ctx, int width, int height, uint64_t s
         const uint64_t n = std::min(batch, spp_count - done);
         a.spp_begin = spp_begin + done;
         a.spp_count = n;
-        CU(ctx, cudaMemsetAsync(ctx->tile_counter.p, 0, sizeof(int), st));
-        CU(ctx, launch_render(ctx->ds, a, ctx->sm_count, st));
-        ctx->stats.kernel_launches++;
+        const bool wavefront = ctx->integrator == 2 || (ctx->integrator == 0 && ctx->ds.bvh_root != BVH_EMPTY_REF);
+        if (wavefront) {
+            CU(ctx, wavefront_render(ctx->ds, a, ctx->wf, ctx->sm_count, (size_t)ctx->wavefront_paths, st, &ctx->stats.kernel_launches));
+        } else {
+            CU(ctx, cudaMemsetAsync(ctx->tile_counter.p, 0, sizeof(int), st));
+            CU(ctx, launch_render(ctx->ds, a, ctx->sm_count, st));
+            ctx->stats.kernel_launches++;
+        }
         done += n;
         if (interactive) {
             CU(ctx, cudaStreamSynchronize(st));

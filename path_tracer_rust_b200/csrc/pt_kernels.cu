@@ -10,94 +10,10 @@
 // "loose" part of the scene (few, large primitives: spheres, wall quads) is staged in shared memory
 // and scanned by all lanes in lock-step (broadcast LDS.128, no divergence); big meshes live in a
 // BVH (pt_bvh.cuh).  No tensor cores: there is no dense contraction in this workload.
-#include "pt_bvh.cuh"
-#include "pt_device.cuh"
 #include "pt_launch.h"
+#include "pt_scene_dev.cuh"
 
 namespace ptb {
-
-constexpr int KIND_SPHERE = 0;
-constexpr float PI_F = 3.141592653589793f;  // mod.rs:29
-constexpr int MAX_DEPTH = 12;               // mod.rs:661
-
-// ---------------------------------------------------------------------------------------------
-// closest hit over the shared-memory ("loose") object list, in the reference's scan order
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void closest_hit_loose(const float4 *__restrict__ s_obj, const float4 *__restrict__ s_tri,
-                                                  int n_obj, V3 o, V3 d, unsigned amask, Hit &best) {
-    for (int i = 0; i < n_obj; ++i) {
-        const float4 sph = s_obj[2 * i];
-        const float4 mb = s_obj[2 * i + 1];
-        const int kind = __float_as_int(mb.x);
-        if (kind == KIND_SPHERE) {
-            const float t = sphere_t(xyz(sph), sph.w, o, d);
-            if (t >= 0.0f && t < best.t) {
-                best.t = t;
-                best.prio = (uint32_t)__float_as_int(mb.y);
-                best.ref = REF_SPHERE_BIT | i;
-            }
-        } else {
-            // mesh: bounding-sphere gate first (mod.rs:267-277); skip the triangle scan if no lane passes
-            const bool pass = sphere_gate(xyz(sph), sph.w, o, d);
-            if (__any_sync(amask, pass)) {
-                const int k0 = __float_as_int(mb.y), k1 = k0 + __float_as_int(mb.z);
-                for (int k = k0; k < k1; ++k) {
-                    const float4 A = s_tri[3 * k], E1 = s_tri[3 * k + 1], E2 = s_tri[3 * k + 2];
-                    const float tt = triangle_t(xyz(A), xyz(E1), xyz(E2), o, d);
-                    if (pass && tt > 0.0f && tt < best.t) {
-                        best.t = tt;
-                        best.prio = (uint32_t)__float_as_int(E2.w);
-                        best.ref = k;
-                    }
-                }
-            }
-        }
-    }
-}
-
-// resolves the winning primitive into (object id, triangle id, hit point, geometric normal)
-__device__ __forceinline__ void finish_hit(const DScene &sc, const float4 *__restrict__ s_obj, const float4 *__restrict__ s_tri,
-                                           const Hit &h, V3 o, V3 d, int &obj, int &tri, V3 &x, V3 &n) {
-    x = o + d * h.t;  // mod.rs:430 / :604
-    const int k = h.ref & (REF_SPHERE_BIT - 1);
-    if (h.ref & REF_BVH_BIT) {
-        const float4 A = __ldg(&sc.bvh_tri[3 * k]), E1 = __ldg(&sc.bvh_tri[3 * k + 1]), E2 = __ldg(&sc.bvh_tri[3 * k + 2]);
-        obj = __float_as_int(A.w);
-        if (h.ref & REF_SPHERE_BIT) { tri = -1; n = normalize(x - xyz(A)); }
-        else { tri = __float_as_int(E1.w); n = normalize(cross(xyz(E1), xyz(E2))); }
-    } else if (h.ref & REF_SPHERE_BIT) {
-        const float4 sph = s_obj[2 * k], mb = s_obj[2 * k + 1];
-        obj = __float_as_int(mb.w);
-        tri = -1;
-        n = normalize(x - xyz(sph));  // mod.rs:431
-    } else {
-        const float4 A = s_tri[3 * k], E1 = s_tri[3 * k + 1], E2 = s_tri[3 * k + 2];
-        obj = __float_as_int(A.w);
-        tri = __float_as_int(E1.w);
-        n = normalize(cross(xyz(E1), xyz(E2)));  // mod.rs:605
-    }
-}
-
-template <bool HAS_BVH>
-__device__ __forceinline__ Hit closest_hit(const DScene &sc, const float4 *__restrict__ s_obj, const float4 *__restrict__ s_tri,
-                                           V3 o, V3 d, unsigned amask) {
-    Hit best;
-    best.t = __int_as_float(0x7f800000);
-    best.prio = PRIO_NONE;
-    best.ref = REF_NONE;
-    closest_hit_loose(s_obj, s_tri, sc.n_loose_obj, o, d, amask, best);
-    if (HAS_BVH) bvh_closest_hit(sc, o, d, best);
-    return best;
-}
-
-__device__ __forceinline__ void stage_loose(const DScene &sc, float4 *smem, const float4 *&s_obj, const float4 *&s_tri) {
-    const int n0 = 2 * sc.n_loose_obj, n1 = 3 * sc.n_loose_tri;
-    for (int i = threadIdx.x; i < n0; i += blockDim.x) smem[i] = __ldg(&sc.loose_obj[i]);
-    for (int i = threadIdx.x; i < n1; i += blockDim.x) smem[n0 + i] = __ldg(&sc.loose_tri[i]);
-    __syncthreads();
-    s_obj = smem;
-    s_tri = smem + n0;
-}
 
 // ---------------------------------------------------------------------------------------------
 // parity hooks: arbitrary rays / deterministic primary rays
@@ -142,7 +58,7 @@ __global__ void __launch_bounds__(256) k_intersect(const DScene sc, const float 
 // ---------------------------------------------------------------------------------------------
 // the integrator megakernel
 // ---------------------------------------------------------------------------------------------
-struct PathStackEntry { V3 o, d, T; int depth; };
+struct PathStackEntry { V3 o, d, T; int depth, code; };
 
 template <bool HAS_BVH>
 __global__ void __launch_bounds__(RENDER_THREADS, RENDER_MIN_BLOCKS) k_render(const DScene sc, const RenderArgs a) {
@@ -177,9 +93,11 @@ __global__ void __launch_bounds__(RENDER_THREADS, RENDER_MIN_BLOCKS) k_render(co
         bool has_path = false, spare_ok = false;
         V3 spare_d = mk3(0.f, 0.f, 1.f);
         V3 o = mk3(0.f, 0.f, 0.f), d = mk3(0.f, 0.f, 1.f), T = mk3(1.f, 1.f, 1.f), L = mk3(0.f, 0.f, 0.f);
-        int depth = 0, sp = 0;
-        uint32_t event = 0, nseg = 0;
+        int depth = 0, sp = 0, code = 0;      // code: which refraction splits were left through the transmitted child
+        unsigned chain_mask = 1u;             // branches of the path tree that exist for this sample
+        uint32_t nseg = 0;
         PathStackEntry stk[2];
+        V3 Lc[4];                             // finished branches' emission sums; radiance = ((L0+L1)+L2)+L3
 
         for (;;) {
             const bool need = valid && !spare_ok && s_next < s_end;
@@ -201,7 +119,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, RENDER_MIN_BLOCKS) k_render(co
             if (!has_path && spare_ok) {  // start sample s = s_next - 1
                 o = sc.lens_center; d = spare_d;
                 T = mk3(1.f, 1.f, 1.f); L = mk3(0.f, 0.f, 0.f);
-                depth = 0; sp = 0; event = 0;
+                depth = 0; sp = 0; code = 0; chain_mask = 1u;
                 s = s_next - 1;
                 spare_ok = false;
                 has_path = true;
@@ -210,82 +128,44 @@ __global__ void __launch_bounds__(RENDER_THREADS, RENDER_MIN_BLOCKS) k_render(co
             if (amask == 0u) break;
             if (has_path) {
                 uint32_t rnd[4];
-                // ---- one radiance() call (mod.rs:662): event k, slots 0 = RR, 1,2 = diffuse, 3 = refraction choice
-                event++;
+                // ---- one radiance() call (mod.rs:662): event (code<<4 | new_depth); slots 0 = RR, 1,2 = diffuse, 3 = refraction
                 nseg++;
-                philox4x32_10(pixel, (uint32_t)s, (uint32_t)(s >> 32), event, k0, k1, rnd);
+                philox4x32_10(pixel, (uint32_t)s, (uint32_t)(s >> 32), ((uint32_t)code << 4) | (uint32_t)(depth + 1), k0, k1, rnd);
                 const Hit h = closest_hit<HAS_BVH>(sc, s_obj, s_tri, o, d, amask);
                 bool cont = false;
                 if (h.ref != REF_NONE) {
                     int obj, tri;
                     V3 x, n;
                     finish_hit(sc, s_obj, s_tri, h, o, d, obj, tri, x, n);
-                    const float4 mc = __ldg(&sc.mat_color[obj]);
-                    const float4 me = __ldg(&sc.mat_emis[obj]);
-                    const int refl = __float_as_int(mc.w);
-                    V3 color = xyz(mc);
-                    const float max_reflection = fmaxf(color.x, fmaxf(color.y, color.z));
-                    const V3 nl = dot(n, d) < 0.0f ? n : n * -1.0f;
                     const int new_depth = depth + 1;
-                    bool alive = true;
-                    if (new_depth > 5) {  // Russian roulette, mod.rs:677-683
-                        if (u32_to_unit(rnd[0]) < max_reflection && new_depth < MAX_DEPTH) color = color * PTB_RCP(max_reflection);
-                        else alive = false;
-                    }
-                    if (__float_as_int(me.w)) L = L + T * xyz(me);
-                    if (alive) {
-                        const V3 Tc = T * color;
-                        if (refl == 0) {  // Diffuse, mod.rs:687-715
-                            const float r1 = 2.0f * PI_F * u32_to_unit(rnd[1]);
-                            const float r2 = u32_to_unit(rnd[2]);
-                            const float r2s = PTB_SQRT(r2);
-                            const V3 w = nl;
-                            const V3 u = normalize(cross(fabsf(w.x) > 0.1f ? mk3(0.f, 1.f, 0.f) : mk3(1.f, 0.f, 0.f), w));
-                            const V3 v = cross(w, u);
-                            float sn, cs;
-                            sincos_det(r1, sn, cs);
-                            d = normalize(u * cs * r2s + v * sn * r2s + w * PTB_SQRT(1.0f - r2));
-                            T = Tc;
-                        } else {
-                            const V3 rd = d - n * 2.0f * dot(n, d);  // mod.rs:722-723
-                            if (refl == 1) {  // Specular
-                                d = rd; T = Tc;
-                            } else {  // Refract, mod.rs:729-788
-                                const bool into = dot(n, nl) > 0.0f;
-                                const float nnt = into ? PTB_DIV(1.0f, 1.5f) : PTB_DIV(1.5f, 1.0f);
-                                const float ddn = dot(d, nl);
-                                const float cos2t = 1.0f - nnt * nnt * (1.0f - ddn * ddn);
-                                if (cos2t < 0.0f) {  // total internal reflection
-                                    d = rd; T = Tc;
-                                } else {
-                                    const V3 tdir = normalize(d * nnt - n * ((into ? 1.0f : -1.0f) * (ddn * nnt + PTB_SQRT(cos2t))));
-                                    const float r0 = PTB_DIV(0.5f * 0.5f, 2.5f * 2.5f);
-                                    const float c = 1.0f - (into ? -ddn : dot(tdir, n));
-                                    const float c2 = c * c;
-                                    const float re = r0 + (1.0f - r0) * (c * (c2 * c2));
-                                    const float tr = 1.0f - re;
-                                    const float p = 0.25f + 0.5f * re;
-                                    if (new_depth > 2) {
-                                        if (u32_to_unit(rnd[3]) < p) { T = Tc * PTB_DIV(re, p); d = rd; }
-                                        else { T = Tc * PTB_DIV(tr, 1.0f - p); d = tdir; }
-                                    } else {  // deterministic two-way split, reflection first (mod.rs:776-785)
-                                        stk[sp].o = x; stk[sp].d = tdir; stk[sp].T = Tc * tr; stk[sp].depth = new_depth;
-                                        sp++;
-                                        T = Tc * re; d = rd;
-                                    }
-                                }
-                            }
+                    ShadeOut so;
+                    shade_hit(sc, obj, n, d, T, new_depth, rnd, so);
+                    if (so.emits) L = L + so.emit;
+                    if (so.cont) {
+                        if (so.split) {  // the reflected child continues this branch, the transmitted one is postponed
+                            const int child = code | (1 << (new_depth - 1));
+                            stk[sp].o = x; stk[sp].d = so.child_d; stk[sp].T = so.child_T; stk[sp].depth = new_depth;
+                            stk[sp].code = child;
+                            chain_mask |= 1u << child;
+                            sp++;
                         }
-                        o = x;
+                        o = x; d = so.d; T = so.T;
                         depth = new_depth;
                         cont = true;
                     }
                 }
                 if (!cont) {
-                    if (sp > 0) {
+                    if (sp > 0) {  // this branch is finished, continue with a postponed transmitted child
+                        Lc[code] = L;
                         sp--;
-                        o = stk[sp].o; d = stk[sp].d; T = stk[sp].T; depth = stk[sp].depth;
+                        o = stk[sp].o; d = stk[sp].d; T = stk[sp].T; depth = stk[sp].depth; code = stk[sp].code;
+                        L = mk3(0.f, 0.f, 0.f);
                     } else {  // sample finished: radiance_v += radiance (mod.rs:846)
+                        if (chain_mask != 1u) {
+                            Lc[code] = L;
+                            const V3 z = mk3(0.f, 0.f, 0.f);
+                            L = ((Lc[0] + ((chain_mask & 2u) ? Lc[1] : z)) + ((chain_mask & 4u) ? Lc[2] : z)) + ((chain_mask & 8u) ? Lc[3] : z);
+                        }
                         acc = acc + L;
                         has_path = false;
                     }

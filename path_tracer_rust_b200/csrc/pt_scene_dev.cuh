@@ -1,0 +1,167 @@
+// pt_scene_dev.cuh -- closest hit over the flattened scene (shared-memory loose list + BVH) and the material arms of
+// radiance(), shared by the megakernel (pt_kernels.cu) and the wavefront integrator (pt_wavefront.cu).
+#pragma once
+#include "pt_bvh.cuh"
+#include "pt_device.cuh"
+
+namespace ptb {
+
+constexpr int KIND_SPHERE = 0;
+constexpr float PI_F = 3.141592653589793f;  // mod.rs:29
+constexpr int MAX_DEPTH = 12;               // mod.rs:661
+
+// ---------------------------------------------------------------------------------------------
+// closest hit over the shared-memory ("loose") object list, in the reference's scan order
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void closest_hit_loose(const float4 *__restrict__ s_obj, const float4 *__restrict__ s_tri,
+                                                  int n_obj, V3 o, V3 d, unsigned amask, Hit &best) {
+    for (int i = 0; i < n_obj; ++i) {
+        const float4 sph = s_obj[2 * i];
+        const float4 mb = s_obj[2 * i + 1];
+        const int kind = __float_as_int(mb.x);
+        if (kind == KIND_SPHERE) {
+            const float t = sphere_t(xyz(sph), sph.w, o, d);
+            if (t >= 0.0f && t < best.t) {
+                best.t = t;
+                best.prio = (uint32_t)__float_as_int(mb.y);
+                best.ref = REF_SPHERE_BIT | i;
+            }
+        } else {
+            // mesh: bounding-sphere gate first (mod.rs:267-277); skip the triangle scan if no lane passes
+            const bool pass = sphere_gate(xyz(sph), sph.w, o, d);
+            if (__any_sync(amask, pass)) {
+                const int k0 = __float_as_int(mb.y), k1 = k0 + __float_as_int(mb.z);
+                for (int k = k0; k < k1; ++k) {
+                    const float4 A = s_tri[3 * k], E1 = s_tri[3 * k + 1], E2 = s_tri[3 * k + 2];
+                    const float tt = triangle_t(xyz(A), xyz(E1), xyz(E2), o, d);
+                    if (pass && tt > 0.0f && tt < best.t) {
+                        best.t = tt;
+                        best.prio = (uint32_t)__float_as_int(E2.w);
+                        best.ref = k;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// resolves the winning primitive into (object id, triangle id, hit point, geometric normal)
+__device__ __forceinline__ void finish_hit(const DScene &sc, const float4 *__restrict__ s_obj, const float4 *__restrict__ s_tri,
+                                           const Hit &h, V3 o, V3 d, int &obj, int &tri, V3 &x, V3 &n) {
+    x = o + d * h.t;  // mod.rs:430 / :604
+    const int k = h.ref & (REF_SPHERE_BIT - 1);
+    if (h.ref & REF_BVH_BIT) {
+        const float4 A = __ldg(&sc.bvh_tri[3 * k]), E1 = __ldg(&sc.bvh_tri[3 * k + 1]), E2 = __ldg(&sc.bvh_tri[3 * k + 2]);
+        obj = __float_as_int(A.w);
+        if (h.ref & REF_SPHERE_BIT) { tri = -1; n = normalize(x - xyz(A)); }
+        else { tri = __float_as_int(E1.w); n = normalize(cross(xyz(E1), xyz(E2))); }
+    } else if (h.ref & REF_SPHERE_BIT) {
+        const float4 sph = s_obj[2 * k], mb = s_obj[2 * k + 1];
+        obj = __float_as_int(mb.w);
+        tri = -1;
+        n = normalize(x - xyz(sph));  // mod.rs:431
+    } else {
+        const float4 A = s_tri[3 * k], E1 = s_tri[3 * k + 1], E2 = s_tri[3 * k + 2];
+        obj = __float_as_int(A.w);
+        tri = __float_as_int(E1.w);
+        n = normalize(cross(xyz(E1), xyz(E2)));  // mod.rs:605
+    }
+}
+
+template <bool HAS_BVH>
+__device__ __forceinline__ Hit closest_hit(const DScene &sc, const float4 *__restrict__ s_obj, const float4 *__restrict__ s_tri,
+                                           V3 o, V3 d, unsigned amask) {
+    Hit best;
+    best.t = __int_as_float(0x7f800000);
+    best.prio = PRIO_NONE;
+    best.ref = REF_NONE;
+    closest_hit_loose(s_obj, s_tri, sc.n_loose_obj, o, d, amask, best);
+    if (HAS_BVH) bvh_closest_hit(sc, o, d, best);
+    return best;
+}
+
+__device__ __forceinline__ void stage_loose(const DScene &sc, float4 *smem, const float4 *&s_obj, const float4 *&s_tri) {
+    const int n0 = 2 * sc.n_loose_obj, n1 = 3 * sc.n_loose_tri;
+    for (int i = threadIdx.x; i < n0; i += blockDim.x) smem[i] = __ldg(&sc.loose_obj[i]);
+    for (int i = threadIdx.x; i < n1; i += blockDim.x) smem[n0 + i] = __ldg(&sc.loose_tri[i]);
+    __syncthreads();
+    s_obj = smem;
+    s_tri = smem + n0;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// one radiance() call after the closest hit is known (mod.rs:665-790), in throughput form.
+// ---------------------------------------------------------------------------------------------
+struct ShadeOut {
+    bool cont;      // the branch continues with (d, T)
+    bool split;     // a transmitted child (child_d, child_T) is spawned (deterministic split, mod.rs:775-786)
+    bool emits;     // emit = T * emission must be added to the branch's sum
+    V3 d, T, child_d, child_T, emit;
+};
+
+__device__ __forceinline__ void shade_hit(const DScene &sc, int obj, V3 n, V3 d_in, V3 T_in, int new_depth, const uint32_t rnd[4],
+                                          ShadeOut &out) {
+    const float4 mc = __ldg(&sc.mat_color[obj]);
+    const float4 me = __ldg(&sc.mat_emis[obj]);
+    const int refl = __float_as_int(mc.w);
+    V3 color = xyz(mc);
+    const float max_reflection = fmaxf(color.x, fmaxf(color.y, color.z));
+    const V3 nl = dot(n, d_in) < 0.0f ? n : n * -1.0f;
+    bool alive = true;
+    if (new_depth > 5) {  // Russian roulette, mod.rs:677-683 (rand01 is drawn before the depth test)
+        if (u32_to_unit(rnd[0]) < max_reflection && new_depth < MAX_DEPTH) color = color * PTB_RCP(max_reflection);
+        else alive = false;
+    }
+    out.emits = __float_as_int(me.w) != 0;
+    out.emit = T_in * xyz(me);
+    out.cont = alive;
+    out.split = false;
+    out.d = d_in; out.T = T_in; out.child_d = d_in; out.child_T = T_in;
+    if (alive) {
+        const V3 Tc = T_in * color;
+        if (refl == 0) {  // Diffuse, mod.rs:687-715
+            const float r1 = 2.0f * PI_F * u32_to_unit(rnd[1]);
+            const float r2 = u32_to_unit(rnd[2]);
+            const float r2s = PTB_SQRT(r2);
+            const V3 w = nl;
+            const V3 u = normalize(cross(fabsf(w.x) > 0.1f ? mk3(0.f, 1.f, 0.f) : mk3(1.f, 0.f, 0.f), w));
+            const V3 v = cross(w, u);
+            float sn, cs;
+            sincos_det(r1, sn, cs);
+            out.d = normalize(u * cs * r2s + v * sn * r2s + w * PTB_SQRT(1.0f - r2));
+            out.T = Tc;
+        } else {
+            const V3 rd = d_in - n * 2.0f * dot(n, d_in);  // mod.rs:722-723
+            if (refl == 1) {  // Specular
+                out.d = rd; out.T = Tc;
+            } else {  // Refract, mod.rs:729-788
+                const bool into = dot(n, nl) > 0.0f;
+                const float nnt = into ? PTB_DIV(1.0f, 1.5f) : PTB_DIV(1.5f, 1.0f);
+                const float ddn = dot(d_in, nl);
+                const float cos2t = 1.0f - nnt * nnt * (1.0f - ddn * ddn);
+                if (cos2t < 0.0f) {  // total internal reflection
+                    out.d = rd; out.T = Tc;
+                } else {
+                    const V3 tdir = normalize(d_in * nnt - n * ((into ? 1.0f : -1.0f) * (ddn * nnt + PTB_SQRT(cos2t))));
+                    const float r0 = PTB_DIV(0.5f * 0.5f, 2.5f * 2.5f);
+                    const float c = 1.0f - (into ? -ddn : dot(tdir, n));
+                    const float c2 = c * c;
+                    const float re = r0 + (1.0f - r0) * (c * (c2 * c2));
+                    const float tr = 1.0f - re;
+                    const float p = 0.25f + 0.5f * re;
+                    if (new_depth > 2) {
+                        if (u32_to_unit(rnd[3]) < p) { out.T = Tc * PTB_DIV(re, p); out.d = rd; }
+                        else { out.T = Tc * PTB_DIV(tr, 1.0f - p); out.d = tdir; }
+                    } else {  // deterministic two-way split (mod.rs:776-785)
+                        out.split = true;
+                        out.child_d = tdir; out.child_T = Tc * tr;
+                        out.T = Tc * re; out.d = rd;
+                    }
+                }
+            }
+        }
+    }
+}
+
+}  // namespace ptb

@@ -1,0 +1,340 @@
+// pt_wavefront.cu -- wavefront integrator for BVH scenes (big meshes / many spheres).
+//
+// Same semantics as the megakernel (pt_kernels.cu) and as the oracle's forward twin: identical Philox events, identical
+// arithmetic, identical per-pixel summation order, hence a bit-identical framebuffer.  What changes is the schedule.
+// In a megakernel every lane walks its own BVH path and the warp runs at the pace of its slowest lane (measured: 6.5 of
+// 32 lanes active).  Here a batch of K samples of every pixel is in flight as a queue of ray segments in HBM and each
+// bounce is two kernels:
+//   k_wf_trace  persistent warps; a lane whose traversal ends writes its hit and is refilled with the next ray of the queue
+//               as soon as REFILL lanes of the warp are idle (Aila & Laine 2009), so traversal runs with mostly full warps;
+//   k_wf_shade  one thread per segment: Philox block, hit point / normal, material arm (shade_hit), appends the continuation
+//               (and the transmitted child of a deterministic refraction split) to the next queue with one warp-aggregated
+//               atomic; a finished branch stores its emission sum in its slot.
+// Branches of a path tree are independent queue entries: event ids depend only on (branch code, depth) and every branch
+// sums its own emission, so nothing depends on the order in which they are processed.  After MAX_DEPTH bounces
+// k_wf_accumulate adds ((L0+L1)+L2)+L3 of samples s0..s0+K-1 to the pixel sum in sample order (mod.rs:846).
+// Queue entries are 4 x float4 (o|path, d|depth+code, T, L) in SoA arrays: coalesced 16-byte loads and stores.
+#include "pt_launch.h"
+#include "pt_scene_dev.cuh"
+#include "pt_wavefront.h"
+
+namespace ptb {
+
+namespace {
+
+constexpr int WF_THREADS = 256;
+constexpr int WF_REFILL = 12;  // idle lanes that trigger a refill of the warp
+
+__global__ void __launch_bounds__(256) k_wf_generate(const DScene sc, int W, int H, unsigned npix, unsigned long long s0, unsigned K,
+                                                     unsigned long long seed, WfQueue q) {
+    const unsigned long long n = (unsigned long long)npix * K;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (unsigned long long p = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
+        const uint32_t pixel = (uint32_t)(p % npix);
+        const unsigned long long s = s0 + p / npix;
+        const int row = (int)(pixel / (uint32_t)W), px = (int)(pixel % (uint32_t)W);
+        uint32_t rnd[4];
+        philox4x32_10(pixel, (uint32_t)s, (uint32_t)(s >> 32), 0u, k0, k1, rnd);  // camera sample: event 0, slots 0,1
+        const float ysub = (float)((s / 2) % 2), xsub = (float)(s % 2);
+        const float r1 = 2.0f * u32_to_unit(rnd[0]);
+        const float r2 = 2.0f * u32_to_unit(rnd[1]);
+        V3 o, d;
+        camera_ray(sc, W, H, px, H - 1 - row, xsub, ysub, tent(r1), tent(r2), o, d);
+        q.o[p] = make_float4(o.x, o.y, o.z, __int_as_float((int)p));
+        q.d[p] = make_float4(d.x, d.y, d.z, __int_as_float(0));
+        q.T[p] = make_float4(1.f, 1.f, 1.f, 0.f);
+        q.L[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+// closest hit of every queued segment
+__global__ void __launch_bounds__(WF_THREADS, 3) k_wf_trace(const DScene sc, const WfQueue q, const int *__restrict__ n_rays_ptr,
+                                                             int *__restrict__ fetch_ptr, float *__restrict__ hit_t,
+                                                             int *__restrict__ hit_ref) {
+    extern __shared__ float4 smem[];
+    const float4 *s_obj, *s_tri;
+    stage_loose(sc, smem, s_obj, s_tri);
+    const int n = *n_rays_ptr;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    bool busy = false, exhausted = false;
+    int ray_idx = 0;
+    V3 o = mk3(0.f, 0.f, 0.f), d = mk3(0.f, 0.f, 1.f), id = mk3(1.f, 1.f, 1.f), ood = mk3(0.f, 0.f, 0.f);
+    Hit best;
+    best.t = 0.f; best.prio = PRIO_NONE; best.ref = REF_NONE;
+    int cur = BVH_EMPTY_REF, sp = 0, gate_obj = -1;
+    bool gate_pass = false;
+    int stack_ref[BVH_STACK];
+    float stack_t[BVH_STACK];
+
+#define PTB_WF_POP()                                                     \
+    do {                                                                 \
+        cur = BVH_EMPTY_REF;                                             \
+        while (sp > 0) {                                                 \
+            --sp;                                                        \
+            if (stack_t[sp] <= best.t) { cur = stack_ref[sp]; break; }   \
+        }                                                                \
+    } while (0)
+
+    for (;;) {
+        const unsigned busy_mask = __ballot_sync(0xffffffffu, busy);
+        const int n_idle = 32 - __popc(busy_mask);
+        if (!exhausted && (n_idle >= WF_REFILL || busy_mask == 0u)) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(fetch_ptr, n_idle);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const int idx = base + __popc(~busy_mask & lt_mask);
+            const bool got = !busy && idx < n;
+            const unsigned got_mask = __ballot_sync(0xffffffffu, got);
+            if (base + n_idle >= n) exhausted = true;
+            if (got) {
+                const float4 qo = __ldg(&q.o[idx]), qd = __ldg(&q.d[idx]);
+                o = mk3(qo.x, qo.y, qo.z); d = mk3(qd.x, qd.y, qd.z);
+                ray_idx = idx;
+                best.t = __int_as_float(0x7f800000); best.prio = PRIO_NONE; best.ref = REF_NONE;
+                closest_hit_loose(s_obj, s_tri, sc.n_loose_obj, o, d, got_mask, best);
+                id = mk3(safe_rcp_dir(d.x), safe_rcp_dir(d.y), safe_rcp_dir(d.z));
+                ood = mk3(o.x * id.x, o.y * id.y, o.z * id.z);
+                cur = sc.bvh_root; sp = 0; gate_obj = -1;
+                busy = true;
+            }
+        }
+        if (__ballot_sync(0xffffffffu, busy) == 0u) break;
+        if (busy) {
+            while (cur >= 0) {  // descend until this lane holds a leaf or is done
+                const float4 *nd = sc.bvh_nodes + 4 * (size_t)cur;
+                const float4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2), n3 = __ldg(nd + 3);
+                float t0, t1;
+                const bool h0 = slab(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, id, ood, best.t, t0);
+                const bool h1 = slab(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, id, ood, best.t, t1);
+                const int r0 = __float_as_int(n3.x), r1 = __float_as_int(n3.y);
+                if (h0 && h1) {
+                    const bool first0 = t0 <= t1;
+                    cur = first0 ? r0 : r1;
+                    stack_ref[sp] = first0 ? r1 : r0;
+                    stack_t[sp] = first0 ? t1 : t0;
+                    sp++;
+                } else if (h0) cur = r0;
+                else if (h1) cur = r1;
+                else PTB_WF_POP();
+            }
+            if (cur != BVH_EMPTY_REF) {
+                const int code = ~cur;
+                const int first = code >> 3, count = (code & 7) + 1;
+                for (int k = first; k < first + count; ++k) {
+                    const float4 A = __ldg(&sc.bvh_tri[3 * k]), E1 = __ldg(&sc.bvh_tri[3 * k + 1]), E2 = __ldg(&sc.bvh_tri[3 * k + 2]);
+                    const bool is_sphere = __float_as_int(E1.w) < 0;
+                    float tt;
+                    if (is_sphere) tt = sphere_t(xyz(A), E1.x, o, d);
+                    else tt = triangle_t(xyz(A), xyz(E1), xyz(E2), o, d);
+                    const uint32_t prio = (uint32_t)__float_as_int(E2.w);
+                    if (tt > 0.0f && (tt < best.t || (tt == best.t && prio < best.prio))) {
+                        bool ok = true;
+                        if (!is_sphere) {  // mesh gate (mod.rs:267-277), lazily, cached per object
+                            const int obj = __float_as_int(A.w);
+                            if (obj != gate_obj) {
+                                const float4 g = __ldg(&sc.obj_gate[obj]);
+                                gate_pass = sphere_gate(xyz(g), g.w, o, d);
+                                gate_obj = obj;
+                            }
+                            ok = gate_pass;
+                        }
+                        if (ok) {
+                            best.t = tt; best.prio = prio;
+                            best.ref = REF_BVH_BIT | (is_sphere ? REF_SPHERE_BIT : 0) | k;
+                        }
+                    }
+                }
+                PTB_WF_POP();
+            }
+            if (cur == BVH_EMPTY_REF) {
+                hit_t[ray_idx] = best.t;
+                hit_ref[ray_idx] = best.ref;
+                busy = false;
+            }
+        }
+    }
+#undef PTB_WF_POP
+}
+
+// material arm of every queued segment; appends the next bounce
+__global__ void __launch_bounds__(256) k_wf_shade(const DScene sc, const WfQueue q, const int *__restrict__ n_rays_ptr,
+                                                  const float *__restrict__ hit_t, const int *__restrict__ hit_ref, WfQueue nq,
+                                                  int *__restrict__ n_next_ptr, float4 *__restrict__ slots, unsigned long long n_paths,
+                                                  unsigned npix, unsigned long long s0, unsigned long long seed,
+                                                  unsigned long long *__restrict__ segment_counter) {
+    extern __shared__ float4 smem[];
+    const float4 *s_obj, *s_tri;
+    stage_loose(sc, smem, s_obj, s_tri);
+    const int n = *n_rays_ptr;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n > 0) atomicAdd(segment_counter, (unsigned long long)n);
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int stride = gridDim.x * blockDim.x;
+    const int n_round = (n + 31) & ~31;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        const bool valid = i < n;
+        int n_out = 0;
+        float4 c_o, c_d, c_T, c_L, k_o, k_d, k_T;  // continuation and (optional) transmitted child
+        if (valid) {
+            const float4 qo = __ldg(&q.o[i]), qd = __ldg(&q.d[i]), qT = __ldg(&q.T[i]), qL = __ldg(&q.L[i]);
+            const int path = __float_as_int(qo.w), dc = __float_as_int(qd.w);
+            const int depth = dc & 0xff, code = dc >> 8;
+            const V3 o = mk3(qo.x, qo.y, qo.z), d = mk3(qd.x, qd.y, qd.z), T = mk3(qT.x, qT.y, qT.z);
+            V3 L = mk3(qL.x, qL.y, qL.z);
+            Hit h;
+            h.t = hit_t[i]; h.ref = hit_ref[i]; h.prio = 0;
+            bool cont = false;
+            if (h.ref != REF_NONE) {
+                const uint32_t pixel = (uint32_t)((unsigned)path % npix);
+                const unsigned long long s = s0 + (unsigned)path / npix;
+                uint32_t rnd[4];
+                philox4x32_10(pixel, (uint32_t)s, (uint32_t)(s >> 32), ((uint32_t)code << 4) | (uint32_t)(depth + 1), k0, k1, rnd);
+                int obj, tri;
+                V3 x, nn;
+                finish_hit(sc, s_obj, s_tri, h, o, d, obj, tri, x, nn);
+                const int new_depth = depth + 1;
+                ShadeOut so;
+                shade_hit(sc, obj, nn, d, T, new_depth, rnd, so);
+                if (so.emits) L = L + so.emit;
+                if (so.cont) {
+                    cont = true;
+                    n_out = 1;
+                    c_o = make_float4(x.x, x.y, x.z, qo.w);
+                    c_d = make_float4(so.d.x, so.d.y, so.d.z, __int_as_float(new_depth | (code << 8)));
+                    c_T = make_float4(so.T.x, so.T.y, so.T.z, 0.f);
+                    c_L = make_float4(L.x, L.y, L.z, 0.f);
+                    if (so.split) {
+                        n_out = 2;
+                        const int child = code | (1 << (new_depth - 1));
+                        k_o = c_o;
+                        k_d = make_float4(so.child_d.x, so.child_d.y, so.child_d.z, __int_as_float(new_depth | (child << 8)));
+                        k_T = make_float4(so.child_T.x, so.child_T.y, so.child_T.z, 0.f);
+                    }
+                }
+            }
+            if (!cont) slots[(size_t)code * n_paths + (size_t)path] = make_float4(L.x, L.y, L.z, 0.f);  // branch finished
+        }
+        // one atomic per warp for all appended entries
+        const unsigned m1 = __ballot_sync(0xffffffffu, n_out >= 1), m2 = __ballot_sync(0xffffffffu, n_out == 2);
+        const int total = __popc(m1) + __popc(m2);
+        if (total) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(n_next_ptr, total);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (n_out >= 1) {
+                const int j = base + __popc(m1 & lt_mask);
+                nq.o[j] = c_o; nq.d[j] = c_d; nq.T[j] = c_T; nq.L[j] = c_L;
+            }
+            if (n_out == 2) {
+                const int j = base + __popc(m1) + __popc(m2 & lt_mask);
+                nq.o[j] = k_o; nq.d[j] = k_d; nq.T[j] = k_T; nq.L[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    }
+}
+
+// radiance_v += radiance(sample) for the K samples of the batch, in sample order (mod.rs:846)
+__global__ void __launch_bounds__(256) k_wf_accumulate(const float4 *__restrict__ slots, unsigned long long n_paths, unsigned npix,
+                                                       unsigned K, float *__restrict__ sum_rgb) {
+    const unsigned stride = gridDim.x * blockDim.x;
+    for (unsigned pixel = blockIdx.x * blockDim.x + threadIdx.x; pixel < npix; pixel += stride) {
+        float *fb = sum_rgb + 3ull * pixel;
+        V3 acc = mk3(fb[0], fb[1], fb[2]);
+        for (unsigned k = 0; k < K; ++k) {
+            const size_t p = (size_t)k * npix + pixel;
+            const float4 a = slots[p], b = slots[n_paths + p], c = slots[2 * n_paths + p], e = slots[3 * n_paths + p];
+            const V3 L = ((mk3(a.x, a.y, a.z) + mk3(b.x, b.y, b.z)) + mk3(c.x, c.y, c.z)) + mk3(e.x, e.y, e.z);
+            acc = acc + L;
+        }
+        fb[0] = acc.x; fb[1] = acc.y; fb[2] = acc.z;
+    }
+}
+
+size_t loose_smem(const DScene &sc) { return sizeof(float4) * (2ull * sc.n_loose_obj + 3ull * sc.n_loose_tri); }
+
+}  // namespace
+
+void wf_release(WfWorkspace &w) {
+    for (int b = 0; b < 2; ++b) {
+        if (w.q[b].o) cudaFree(w.q[b].o);
+        if (w.q[b].d) cudaFree(w.q[b].d);
+        if (w.q[b].T) cudaFree(w.q[b].T);
+        if (w.q[b].L) cudaFree(w.q[b].L);
+    }
+    if (w.hit_t) cudaFree(w.hit_t);
+    if (w.hit_ref) cudaFree(w.hit_ref);
+    if (w.slots) cudaFree(w.slots);
+    if (w.counters) cudaFree(w.counters);
+    w = WfWorkspace{};
+}
+
+static cudaError_t wf_reserve(WfWorkspace &w, size_t n_paths) {
+    if (n_paths <= w.cap_paths) return cudaSuccess;
+    wf_release(w);
+    const size_t cap = 4 * n_paths;  // every path can split twice (mod.rs:775-786): at most 4 live branches
+    cudaError_t e;
+    for (int b = 0; b < 2; ++b) {
+        if ((e = cudaMalloc((void **)&w.q[b].o, cap * sizeof(float4))) != cudaSuccess) return e;
+        if ((e = cudaMalloc((void **)&w.q[b].d, cap * sizeof(float4))) != cudaSuccess) return e;
+        if ((e = cudaMalloc((void **)&w.q[b].T, cap * sizeof(float4))) != cudaSuccess) return e;
+        if ((e = cudaMalloc((void **)&w.q[b].L, cap * sizeof(float4))) != cudaSuccess) return e;
+    }
+    if ((e = cudaMalloc((void **)&w.hit_t, cap * sizeof(float))) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void **)&w.hit_ref, cap * sizeof(int))) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void **)&w.slots, 4 * n_paths * sizeof(float4))) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void **)&w.counters, 2 * (WF_MAX_BOUNCES + 2) * sizeof(int))) != cudaSuccess) return e;
+    w.cap_paths = n_paths;
+    return cudaSuccess;
+}
+
+// renders samples [a.spp_begin, a.spp_begin + a.spp_count) of every pixel into a.sum_rgb; returns the number of kernels launched
+cudaError_t wavefront_render(const DScene &sc, const RenderArgs &a, WfWorkspace &w, int sm_count, size_t target_paths, cudaStream_t st,
+                             unsigned *launches) {
+    const unsigned npix = (unsigned)a.width * (unsigned)a.height;
+    unsigned K = (unsigned)std::max<size_t>(1, target_paths / npix);
+    if ((unsigned long long)K > a.spp_count) K = (unsigned)a.spp_count;
+    if (K == 0) return cudaSuccess;
+    const size_t n_paths = (size_t)npix * K;
+    if (n_paths > (1ull << 29)) return cudaErrorInvalidValue;  // queue indices are 32-bit ints, 4 branches per path
+    cudaError_t e = wf_reserve(w, n_paths);
+    if (e != cudaSuccess) return e;
+    const size_t smem = loose_smem(sc);
+    if ((e = cudaFuncSetAttribute(k_wf_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_wf_shade, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    int trace_per_sm = 0;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_per_sm, k_wf_trace, WF_THREADS, smem)) != cudaSuccess) return e;
+    if (trace_per_sm < 1) return cudaErrorLaunchOutOfResources;
+    const int trace_blocks = sm_count * trace_per_sm, wide_blocks = sm_count * 8;
+
+    unsigned long long done = 0;
+    while (done < a.spp_count) {
+        const unsigned k_now = (unsigned)std::min<unsigned long long>(K, a.spp_count - done);
+        const size_t paths_now = (size_t)npix * k_now;
+        const unsigned long long s0 = a.spp_begin + done;
+        // counters[2*b] = entries of bounce b's queue, counters[2*b+1] = its fetch cursor
+        if ((e = cudaMemsetAsync(w.counters, 0, 2 * (WF_MAX_BOUNCES + 2) * sizeof(int), st)) != cudaSuccess) return e;
+        const int first = (int)paths_now;
+        if ((e = cudaMemcpyAsync(w.counters, &first, sizeof(int), cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(w.slots, 0, 4 * n_paths * sizeof(float4), st)) != cudaSuccess) return e;
+        k_wf_generate<<<wide_blocks, 256, 0, st>>>(sc, a.width, a.height, npix, s0, k_now, a.seed, w.q[0]);
+        (*launches)++;
+        for (int b = 0; b < WF_MAX_BOUNCES; ++b) {
+            const WfQueue &cur = w.q[b & 1], &nxt = w.q[(b + 1) & 1];
+            k_wf_trace<<<trace_blocks, WF_THREADS, smem, st>>>(sc, cur, w.counters + 2 * b, w.counters + 2 * b + 1, w.hit_t, w.hit_ref);
+            k_wf_shade<<<wide_blocks, 256, smem, st>>>(sc, cur, w.counters + 2 * b, w.hit_t, w.hit_ref, nxt, w.counters + 2 * (b + 1), w.slots,
+                                                       n_paths, npix, s0, a.seed, a.segment_counter);
+            *launches += 2;
+        }
+        k_wf_accumulate<<<wide_blocks, 256, 0, st>>>(w.slots, n_paths, npix, k_now, a.sum_rgb);
+        (*launches)++;
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        done += k_now;
+    }
+    return cudaSuccess;
+}
+
+}  // namespace ptb

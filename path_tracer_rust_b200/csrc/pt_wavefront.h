@@ -1,0 +1,34 @@
+// pt_wavefront.h -- host interface of the wavefront integrator (internal)
+#pragma once
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstddef>
+
+#include "pt_launch.h"
+
+namespace ptb {
+
+constexpr int WF_MAX_BOUNCES = 12;  // = MAX_DEPTH (mod.rs:661): a branch makes at most 12 radiance() calls
+
+struct WfQueue {   // SoA of ray segments: 4 x float4 per entry
+    float4 *o = nullptr;  // origin | path id (sample offset * npix + pixel)
+    float4 *d = nullptr;  // direction | depth + (branch code << 8)
+    float4 *T = nullptr;  // throughput
+    float4 *L = nullptr;  // emission sum of the branch so far
+};
+
+struct WfWorkspace {
+    WfQueue q[2];
+    float *hit_t = nullptr;
+    int *hit_ref = nullptr;
+    float4 *slots = nullptr;  // [4 branches][n_paths] finished branch sums
+    int *counters = nullptr;  // per bounce: queue length, fetch cursor
+    size_t cap_paths = 0;
+};
+
+void wf_release(WfWorkspace &w);
+cudaError_t wavefront_render(const DScene &sc, const RenderArgs &a, WfWorkspace &w, int sm_count, size_t target_paths, cudaStream_t st,
+                             unsigned *launches);
+
+}  // namespace ptb

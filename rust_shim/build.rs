@@ -14,7 +14,7 @@ fn main() {
     let status = Command::new("nvcc")
         .args(flags)
         .arg("-o").arg(&lib)
-        .args(["pt_kernels.cu", "pt_bvh_build.cu", "pt_api.cu"].iter().map(|f| src.join(f)))
+        .args(["pt_kernels.cu", "pt_wavefront.cu", "pt_bvh_build.cu", "pt_api.cu"].iter().map(|f| src.join(f)))
         .arg("-x").arg("cu").arg(src.join("scene_io.cpp"))
         .status().expect("nvcc not found");
     assert!(status.success(), "nvcc failed");

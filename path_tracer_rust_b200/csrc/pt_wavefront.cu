@@ -23,14 +23,29 @@ namespace ptb {
 namespace {
 
 constexpr int WF_THREADS = 256;
-constexpr int WF_REFILL = 12;  // idle lanes that trigger a refill of the warp
+constexpr int WF_REFILL = 8;        // idle lanes that trigger a refill of the warp
+constexpr int WF_DESCEND_MIN = 12;  // leave the inner-node loop when fewer lanes than this are still descending
+
+__device__ __forceinline__ void store_loose_hit(const WfQueue &q, size_t j, const float4 *s_obj, const float4 *s_tri, int n_loose,
+                                                V3 o, V3 d, unsigned amask) {
+    Hit best;
+    best.t = __int_as_float(0x7f800000); best.prio = PRIO_NONE; best.ref = REF_NONE;
+    closest_hit_loose(s_obj, s_tri, n_loose, o, d, amask, best);
+    q.hit_t[j] = best.t; q.hit_ref[j] = best.ref; q.hit_prio[j] = best.prio;
+}
 
 __global__ void __launch_bounds__(256) k_wf_generate(const DScene sc, int W, int H, unsigned npix, unsigned long long s0, unsigned K,
                                                      unsigned long long seed, WfQueue q) {
+    extern __shared__ float4 smem[];
+    const float4 *s_obj, *s_tri;
+    stage_loose(sc, smem, s_obj, s_tri);
     const unsigned long long n = (unsigned long long)npix * K;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-    for (unsigned long long p = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
+    const unsigned long long n_round = (n + 31ull) & ~31ull;
+    for (unsigned long long p = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; p < n_round; p += stride) {
+        const unsigned amask = __ballot_sync(0xffffffffu, p < n);
+        if (p >= n) continue;
         const uint32_t pixel = (uint32_t)(p % npix);
         const unsigned long long s = s0 + p / npix;
         const int row = (int)(pixel / (uint32_t)W), px = (int)(pixel % (uint32_t)W);
@@ -45,16 +60,13 @@ __global__ void __launch_bounds__(256) k_wf_generate(const DScene sc, int W, int
         q.d[p] = make_float4(d.x, d.y, d.z, __int_as_float(0));
         q.T[p] = make_float4(1.f, 1.f, 1.f, 0.f);
         q.L[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+        store_loose_hit(q, p, s_obj, s_tri, sc.n_loose_obj, o, d, amask);
     }
 }
 
 // closest hit of every queued segment
 __global__ void __launch_bounds__(WF_THREADS, 3) k_wf_trace(const DScene sc, const WfQueue q, const int *__restrict__ n_rays_ptr,
-                                                             int *__restrict__ fetch_ptr, float *__restrict__ hit_t,
-                                                             int *__restrict__ hit_ref) {
-    extern __shared__ float4 smem[];
-    const float4 *s_obj, *s_tri;
-    stage_loose(sc, smem, s_obj, s_tri);
+                                                             int *__restrict__ fetch_ptr) {
     const int n = *n_rays_ptr;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -87,14 +99,12 @@ __global__ void __launch_bounds__(WF_THREADS, 3) k_wf_trace(const DScene sc, con
             base = __shfl_sync(0xffffffffu, base, 0);
             const int idx = base + __popc(~busy_mask & lt_mask);
             const bool got = !busy && idx < n;
-            const unsigned got_mask = __ballot_sync(0xffffffffu, got);
             if (base + n_idle >= n) exhausted = true;
             if (got) {
                 const float4 qo = __ldg(&q.o[idx]), qd = __ldg(&q.d[idx]);
                 o = mk3(qo.x, qo.y, qo.z); d = mk3(qd.x, qd.y, qd.z);
                 ray_idx = idx;
-                best.t = __int_as_float(0x7f800000); best.prio = PRIO_NONE; best.ref = REF_NONE;
-                closest_hit_loose(s_obj, s_tri, sc.n_loose_obj, o, d, got_mask, best);
+                best.t = q.hit_t[idx]; best.ref = q.hit_ref[idx]; best.prio = q.hit_prio[idx];
                 id = mk3(safe_rcp_dir(d.x), safe_rcp_dir(d.y), safe_rcp_dir(d.z));
                 ood = mk3(o.x * id.x, o.y * id.y, o.z * id.z);
                 cur = sc.bvh_root; sp = 0; gate_obj = -1;
@@ -119,8 +129,9 @@ __global__ void __launch_bounds__(WF_THREADS, 3) k_wf_trace(const DScene sc, con
                 } else if (h0) cur = r0;
                 else if (h1) cur = r1;
                 else PTB_WF_POP();
+                if (__popc(__activemask()) < WF_DESCEND_MIN) break;  // let the lanes that hold a leaf get on with it
             }
-            if (cur != BVH_EMPTY_REF) {
+            if (cur < 0 && cur != BVH_EMPTY_REF) {
                 const int code = ~cur;
                 const int first = code >> 3, count = (code & 7) + 1;
                 for (int k = first; k < first + count; ++k) {
@@ -150,8 +161,8 @@ __global__ void __launch_bounds__(WF_THREADS, 3) k_wf_trace(const DScene sc, con
                 PTB_WF_POP();
             }
             if (cur == BVH_EMPTY_REF) {
-                hit_t[ray_idx] = best.t;
-                hit_ref[ray_idx] = best.ref;
+                q.hit_t[ray_idx] = best.t;
+                q.hit_ref[ray_idx] = best.ref;
                 busy = false;
             }
         }
@@ -160,8 +171,7 @@ __global__ void __launch_bounds__(WF_THREADS, 3) k_wf_trace(const DScene sc, con
 }
 
 // material arm of every queued segment; appends the next bounce
-__global__ void __launch_bounds__(256) k_wf_shade(const DScene sc, const WfQueue q, const int *__restrict__ n_rays_ptr,
-                                                  const float *__restrict__ hit_t, const int *__restrict__ hit_ref, WfQueue nq,
+__global__ void __launch_bounds__(256) k_wf_shade(const DScene sc, const WfQueue q, const int *__restrict__ n_rays_ptr, WfQueue nq,
                                                   int *__restrict__ n_next_ptr, float4 *__restrict__ slots, unsigned long long n_paths,
                                                   unsigned npix, unsigned long long s0, unsigned long long seed,
                                                   unsigned long long *__restrict__ segment_counter) {
@@ -186,7 +196,7 @@ __global__ void __launch_bounds__(256) k_wf_shade(const DScene sc, const WfQueue
             const V3 o = mk3(qo.x, qo.y, qo.z), d = mk3(qd.x, qd.y, qd.z), T = mk3(qT.x, qT.y, qT.z);
             V3 L = mk3(qL.x, qL.y, qL.z);
             Hit h;
-            h.t = hit_t[i]; h.ref = hit_ref[i]; h.prio = 0;
+            h.t = q.hit_t[i]; h.ref = q.hit_ref[i]; h.prio = 0;
             bool cont = false;
             if (h.ref != REF_NONE) {
                 const uint32_t pixel = (uint32_t)((unsigned)path % npix);
@@ -228,10 +238,12 @@ __global__ void __launch_bounds__(256) k_wf_shade(const DScene sc, const WfQueue
             if (n_out >= 1) {
                 const int j = base + __popc(m1 & lt_mask);
                 nq.o[j] = c_o; nq.d[j] = c_d; nq.T[j] = c_T; nq.L[j] = c_L;
+                store_loose_hit(nq, j, s_obj, s_tri, sc.n_loose_obj, mk3(c_o.x, c_o.y, c_o.z), mk3(c_d.x, c_d.y, c_d.z), m1);
             }
             if (n_out == 2) {
                 const int j = base + __popc(m1) + __popc(m2 & lt_mask);
                 nq.o[j] = k_o; nq.d[j] = k_d; nq.T[j] = k_T; nq.L[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                store_loose_hit(nq, j, s_obj, s_tri, sc.n_loose_obj, mk3(k_o.x, k_o.y, k_o.z), mk3(k_d.x, k_d.y, k_d.z), m2);
             }
         }
     }
@@ -264,9 +276,10 @@ void wf_release(WfWorkspace &w) {
         if (w.q[b].d) cudaFree(w.q[b].d);
         if (w.q[b].T) cudaFree(w.q[b].T);
         if (w.q[b].L) cudaFree(w.q[b].L);
+        if (w.q[b].hit_t) cudaFree(w.q[b].hit_t);
+        if (w.q[b].hit_ref) cudaFree(w.q[b].hit_ref);
+        if (w.q[b].hit_prio) cudaFree(w.q[b].hit_prio);
     }
-    if (w.hit_t) cudaFree(w.hit_t);
-    if (w.hit_ref) cudaFree(w.hit_ref);
     if (w.slots) cudaFree(w.slots);
     if (w.counters) cudaFree(w.counters);
     w = WfWorkspace{};
@@ -282,9 +295,10 @@ static cudaError_t wf_reserve(WfWorkspace &w, size_t n_paths) {
         if ((e = cudaMalloc((void **)&w.q[b].d, cap * sizeof(float4))) != cudaSuccess) return e;
         if ((e = cudaMalloc((void **)&w.q[b].T, cap * sizeof(float4))) != cudaSuccess) return e;
         if ((e = cudaMalloc((void **)&w.q[b].L, cap * sizeof(float4))) != cudaSuccess) return e;
+        if ((e = cudaMalloc((void **)&w.q[b].hit_t, cap * sizeof(float))) != cudaSuccess) return e;
+        if ((e = cudaMalloc((void **)&w.q[b].hit_ref, cap * sizeof(int))) != cudaSuccess) return e;
+        if ((e = cudaMalloc((void **)&w.q[b].hit_prio, cap * sizeof(unsigned))) != cudaSuccess) return e;
     }
-    if ((e = cudaMalloc((void **)&w.hit_t, cap * sizeof(float))) != cudaSuccess) return e;
-    if ((e = cudaMalloc((void **)&w.hit_ref, cap * sizeof(int))) != cudaSuccess) return e;
     if ((e = cudaMalloc((void **)&w.slots, 4 * n_paths * sizeof(float4))) != cudaSuccess) return e;
     if ((e = cudaMalloc((void **)&w.counters, 2 * (WF_MAX_BOUNCES + 2) * sizeof(int))) != cudaSuccess) return e;
     w.cap_paths = n_paths;
@@ -303,10 +317,10 @@ cudaError_t wavefront_render(const DScene &sc, const RenderArgs &a, WfWorkspace 
     cudaError_t e = wf_reserve(w, n_paths);
     if (e != cudaSuccess) return e;
     const size_t smem = loose_smem(sc);
-    if ((e = cudaFuncSetAttribute(k_wf_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_wf_generate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_wf_shade, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     int trace_per_sm = 0;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_per_sm, k_wf_trace, WF_THREADS, smem)) != cudaSuccess) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_per_sm, k_wf_trace, WF_THREADS, 0)) != cudaSuccess) return e;
     if (trace_per_sm < 1) return cudaErrorLaunchOutOfResources;
     const int trace_blocks = sm_count * trace_per_sm, wide_blocks = sm_count * 8;
 
@@ -320,12 +334,12 @@ cudaError_t wavefront_render(const DScene &sc, const RenderArgs &a, WfWorkspace 
         const int first = (int)paths_now;
         if ((e = cudaMemcpyAsync(w.counters, &first, sizeof(int), cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
         if ((e = cudaMemsetAsync(w.slots, 0, 4 * n_paths * sizeof(float4), st)) != cudaSuccess) return e;
-        k_wf_generate<<<wide_blocks, 256, 0, st>>>(sc, a.width, a.height, npix, s0, k_now, a.seed, w.q[0]);
+        k_wf_generate<<<wide_blocks, 256, smem, st>>>(sc, a.width, a.height, npix, s0, k_now, a.seed, w.q[0]);
         (*launches)++;
         for (int b = 0; b < WF_MAX_BOUNCES; ++b) {
             const WfQueue &cur = w.q[b & 1], &nxt = w.q[(b + 1) & 1];
-            k_wf_trace<<<trace_blocks, WF_THREADS, smem, st>>>(sc, cur, w.counters + 2 * b, w.counters + 2 * b + 1, w.hit_t, w.hit_ref);
-            k_wf_shade<<<wide_blocks, 256, smem, st>>>(sc, cur, w.counters + 2 * b, w.hit_t, w.hit_ref, nxt, w.counters + 2 * (b + 1), w.slots,
+            k_wf_trace<<<trace_blocks, WF_THREADS, 0, st>>>(sc, cur, w.counters + 2 * b, w.counters + 2 * b + 1);
+            k_wf_shade<<<wide_blocks, 256, smem, st>>>(sc, cur, w.counters + 2 * b, nxt, w.counters + 2 * (b + 1), w.slots,
                                                        n_paths, npix, s0, a.seed, a.segment_counter);
             *launches += 2;
         }

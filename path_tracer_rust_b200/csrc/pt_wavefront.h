@@ -16,12 +16,15 @@ struct WfQueue {   // SoA of ray segments: 4 x float4 per entry
     float4 *d = nullptr;  // direction | depth + (branch code << 8)
     float4 *T = nullptr;  // throughput
     float4 *L = nullptr;  // emission sum of the branch so far
+    // closest hit so far: initialised with the shared-memory ("loose") part of the scene by the kernel that creates the
+    // segment (all lanes converged there), completed by k_wf_trace with the BVH part, consumed by k_wf_shade
+    float *hit_t = nullptr;
+    int *hit_ref = nullptr;
+    unsigned *hit_prio = nullptr;
 };
 
 struct WfWorkspace {
     WfQueue q[2];
-    float *hit_t = nullptr;
-    int *hit_ref = nullptr;
     float4 *slots = nullptr;  // [4 branches][n_paths] finished branch sums
     int *counters = nullptr;  // per bounce: queue length, fetch cursor
     size_t cap_paths = 0;

@@ -15,9 +15,10 @@ constexpr int MAX_DEPTH = 12;               // mod.rs:661
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void closest_hit_loose(const float4 *__restrict__ s_obj, const float4 *__restrict__ s_tri,
                                                   int n_obj, V3 o, V3 d, unsigned amask, Hit &best) {
-    for (int i = 0; i < n_obj; ++i) {
-        const float4 sph = s_obj[2 * i];
-        const float4 mb = s_obj[2 * i + 1];
+    const float4 *rec = s_obj;
+    for (int i = 0; i < n_obj; ++i, rec += 2) {
+        const float4 sph = rec[0];
+        const float4 mb = rec[1];
         const int kind = __float_as_int(mb.x);
         if (kind == KIND_SPHERE) {
             const float t = sphere_t(xyz(sph), sph.w, o, d);
@@ -30,15 +31,20 @@ __device__ __forceinline__ void closest_hit_loose(const float4 *__restrict__ s_o
             // mesh: bounding-sphere gate first (mod.rs:267-277); skip the triangle scan if no lane passes
             const bool pass = sphere_gate(xyz(sph), sph.w, o, d);
             if (__any_sync(amask, pass)) {
-                const int k0 = __float_as_int(mb.y), k1 = k0 + __float_as_int(mb.z);
-                for (int k = k0; k < k1; ++k) {
-                    const float4 A = s_tri[3 * k], E1 = s_tri[3 * k + 1], E2 = s_tri[3 * k + 2];
-                    const float tt = triangle_t(xyz(A), xyz(E1), xyz(E2), o, d);
-                    if (pass && tt > 0.0f && tt < best.t) {
-                        best.t = tt;
-                        best.prio = (uint32_t)__float_as_int(E2.w);
-                        best.ref = k;
-                    }
+                int k = __float_as_int(mb.y);
+                const int k1 = k + __float_as_int(mb.z);
+                const float4 *tr = s_tri + 3 * k;
+                for (; k + 1 < k1; k += 2, tr += 6) {  // two triangles per trip (wall quads)
+                    float ta, tb;
+                    const bool ha = triangle_hit(xyz(tr[0]), xyz(tr[1]), xyz(tr[2]), o, d, ta);
+                    const bool hb = triangle_hit(xyz(tr[3]), xyz(tr[4]), xyz(tr[5]), o, d, tb);
+                    if (pass && ha && ta < best.t) { best.t = ta; best.prio = (uint32_t)__float_as_int(tr[2].w); best.ref = k; }
+                    if (pass && hb && tb < best.t) { best.t = tb; best.prio = (uint32_t)__float_as_int(tr[5].w); best.ref = k + 1; }
+                }
+                if (k < k1) {
+                    float ta;
+                    const bool ha = triangle_hit(xyz(tr[0]), xyz(tr[1]), xyz(tr[2]), o, d, ta);
+                    if (pass && ha && ta < best.t) { best.t = ta; best.prio = (uint32_t)__float_as_int(tr[2].w); best.ref = k; }
                 }
             }
         }

@@ -283,10 +283,22 @@ def main():
             cpu = cpu_reference_run(scene_id, W, H, 12.0)
         # roofline of the dominant kernel (k_render): FP32 issue slots.  Algorithmic flops per segment follow SURVEY.md 8d:
         # 17 per sphere/gate test + 45 per triangle test + 120 shading, with the reference algorithm's own test counts.
-        tps = cpu["tests_per_segment"] if cpu else None
-        if tps is None or scene_id == "synthetic":
-            tps = {"sphere": 4.0, "gate": 7.0, "triangle": 11.0} if scene_id == "cornell" else {"sphere": 0, "gate": 0, "triangle": 0}
-        flops_per_seg = 17.0 * (tps["sphere"] + tps["gate"]) + 45.0 * tps["triangle"] + 120.0
+        st_last = be.stats()
+        if st_last["n_bvh_nodes"] > 0 and st_last["segments"] > 0:
+            # BVH scene: device-counted work of the last step (wavefront integrator): every segment scans the shared-memory list,
+            # then visits bvh_nodes_visited inner nodes (30 flops each: two slab tests) and tests bvh_prims_tested primitives
+            seg_last = float(st_last["segments"])
+            tps = {"sphere": 0.0, "gate": float(st_last["n_loose_objects"]),
+                   "triangle": float(st_last["n_loose_triangles"]) + st_last["bvh_prims_tested"] / seg_last,
+                   "bvh_nodes": st_last["bvh_nodes_visited"] / seg_last}
+            dominant = "k_wf_trace (+ k_wf_shade, k_wf_generate, k_wf_accumulate; whole wavefront pipeline timed)"
+        else:
+            tps = cpu["tests_per_segment"] if cpu else None
+            if tps is None:
+                tps = {"sphere": 4.0, "gate": 7.0, "triangle": 11.0} if scene_id == "cornell" else {"sphere": 0, "gate": 0, "triangle": 0}
+            tps = dict(tps, bvh_nodes=0.0)
+            dominant = "k_render"
+        flops_per_seg = 17.0 * (tps["sphere"] + tps["gate"]) + 45.0 * tps["triangle"] + 30.0 * tps["bvh_nodes"] + 120.0
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
         fp32_peak = sms * 128 * peaks["sm_max_mhz"] * 1e6 * 1e-12          # T lane-ops/s, un-fused (FMA is barred by parity)
         seg_per_gpu = seg_total / max(world, 1) / args.steps
@@ -307,7 +319,7 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "fp32_issue", "achieved": achieved, "peak": fp32_peak, "unit": "Tlane-op/s",
                          "frac": (achieved / fp32_peak) if achieved else None, "traffic": None,
-                         "kernel": "k_render", "flops_per_segment": flops_per_seg, "kernel_ms": kernel_ms_last,
+                         "kernel": dominant, "flops_per_segment": flops_per_seg, "tests_per_segment": tps, "kernel_ms": kernel_ms_last,
                          "peak_source": f"SMs({sms}) x 128 lanes x sm_max_mhz({peaks['sm_max_mhz']}) from MEASURED_PEAKS.json ({peaks['source']}); "
                                         "no tensor or HBM bound applies: scene and path state live in shared memory / registers"},
             "cpu_baseline": ({"value": cpu["mpaths_s"], "unit": "Mpaths/s", "cores": cpu["threads"], "kind": "port",

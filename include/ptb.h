@@ -83,6 +83,8 @@ typedef struct ptb_stats {
     uint32_t kernel_launches; /* kernels launched by the last render / query call */
     uint32_t n_loose_objects, n_loose_triangles;   /* brute-force (shared-memory) part of the scene */
     uint32_t n_bvh_triangles, n_bvh_spheres, n_bvh_nodes;
+    uint64_t bvh_nodes_visited;  /* last render (wavefront integrator): inner BVH nodes fetched */
+    uint64_t bvh_prims_tested;   /* last render (wavefront integrator): leaf primitives tested */
 } ptb_stats;
 
 /* ---- host-side scene I/O: SceneDescriptor::load + to_data (mod.rs:92-110, 304-318), load_off.rs:8-85 ---- */

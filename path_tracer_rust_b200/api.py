@@ -56,7 +56,7 @@ class Stats(C.Structure):
     _fields_ = [("segments", C.c_uint64), ("samples", C.c_uint64), ("render_ms", C.c_double), ("upload_ms", C.c_double),
                 ("bvh_build_ms", C.c_double), ("kernel_launches", C.c_uint32), ("n_loose_objects", C.c_uint32),
                 ("n_loose_triangles", C.c_uint32), ("n_bvh_triangles", C.c_uint32), ("n_bvh_spheres", C.c_uint32),
-                ("n_bvh_nodes", C.c_uint32)]
+                ("n_bvh_nodes", C.c_uint32), ("bvh_nodes_visited", C.c_uint64), ("bvh_prims_tested", C.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -201,7 +201,7 @@ extern "C" int ptb_create(int device_id, ptb_ctx **out) {
     if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = ctx->tile_counter.resize(1)) != cudaSuccess) return bail(e, "cudaMalloc");
-    if ((e = ctx->seg_counter.resize(1)) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = ctx->seg_counter.resize(4)) != cudaSuccess) return bail(e, "cudaMalloc");  // segments, BVH nodes, BVH prims, -
     // parity self-test: the kernels must have been built with --fmad=false
     if ((e = ctx->scratch_f.resize(4)) != cudaSuccess) return bail(e, "cudaMalloc");
     const float a = 1.0f + 1.0f / 8192.0f, c = -(1.0f + 1.0f / 4096.0f);
@@ -369,10 +369,12 @@ extern "C" int ptb_get_stats(const ptb_ctx *ctx, ptb_stats *out) {
         CU(m, cudaStreamSynchronize(ctx->pending_stream));
         float ms = 0.f;
         CU(m, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-        unsigned long long seg = 0;
-        CU(m, cudaMemcpy(&seg, ctx->seg_counter.p, sizeof seg, cudaMemcpyDeviceToHost));
+        unsigned long long cnt[4] = {0, 0, 0, 0};
+        CU(m, cudaMemcpy(cnt, ctx->seg_counter.p, sizeof cnt, cudaMemcpyDeviceToHost));
         m->stats.render_ms = ms;
-        m->stats.segments = seg;
+        m->stats.segments = cnt[0];
+        m->stats.bvh_nodes_visited = cnt[1];
+        m->stats.bvh_prims_tested = cnt[2];
         ctx->stats_pending = false;
     }
     *out = ctx->stats;
@@ -403,7 +405,7 @@ extern "C" int ptb_render_device(ptb_ctx *ctx, int width, int height, uint64_t s
 
     ctx->stats.kernel_launches = 0;
     ctx->stats.samples = 0;
-    CU(ctx, cudaMemsetAsync(ctx->seg_counter.p, 0, sizeof(unsigned long long), st));
+    CU(ctx, cudaMemsetAsync(ctx->seg_counter.p, 0, 4 * sizeof(unsigned long long), st));
     CU(ctx, cudaEventRecord(ctx->ev0, st));
     const uint64_t npix = static_cast<uint64_t>(width) * static_cast<uint64_t>(height);
     // batch size: bounded work per launch so cancel / progress stay responsive (samples per launch ~ 2^31)
@@ -436,9 +438,11 @@ extern "C" int ptb_render_device(ptb_ctx *ctx, int width, int height, uint64_t s
         float ms = 0.f;
         CU(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
         ctx->stats.render_ms = ms;
-        unsigned long long seg = 0;
-        CU(ctx, cudaMemcpy(&seg, ctx->seg_counter.p, sizeof seg, cudaMemcpyDeviceToHost));
-        ctx->stats.segments = seg;
+        unsigned long long cnt[4] = {0, 0, 0, 0};
+        CU(ctx, cudaMemcpy(cnt, ctx->seg_counter.p, sizeof cnt, cudaMemcpyDeviceToHost));
+        ctx->stats.segments = cnt[0];
+        ctx->stats.bvh_nodes_visited = cnt[1];
+        ctx->stats.bvh_prims_tested = cnt[2];
         ctx->stats_pending = false;
     } else {
         ctx->stats_pending = true;

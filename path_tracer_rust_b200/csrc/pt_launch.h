@@ -19,7 +19,7 @@ struct RenderArgs {
     float *sum_rgb;                        // W*H*3 fp32 running sum, reference index order
     int *tile_counter;                     // zeroed before each launch
     int n_tiles, tiles_x;
-    unsigned long long *segment_counter;   // += closest-hit queries
+    unsigned long long *segment_counter;   // [0] += closest-hit queries, [1] += BVH nodes fetched, [2] += BVH primitives tested
 };
 
 cudaError_t launch_rcp_selftest(unsigned long long *d_mismatches, int sm_count, cudaStream_t st);

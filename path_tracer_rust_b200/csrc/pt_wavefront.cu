@@ -66,8 +66,9 @@ __global__ void __launch_bounds__(256) k_wf_generate(const DScene sc, int W, int
 
 // closest hit of every queued segment
 __global__ void __launch_bounds__(WF_THREADS, 3) k_wf_trace(const DScene sc, const WfQueue q, const int *__restrict__ n_rays_ptr,
-                                                             int *__restrict__ fetch_ptr) {
+                                                             int *__restrict__ fetch_ptr, unsigned long long *__restrict__ counters) {
     const int n = *n_rays_ptr;
+    unsigned n_nodes = 0, n_prims = 0;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
 
@@ -116,6 +117,7 @@ __global__ void __launch_bounds__(WF_THREADS, 3) k_wf_trace(const DScene sc, con
             while (cur >= 0) {  // descend until this lane holds a leaf or is done
                 const float4 *nd = sc.bvh_nodes + 4 * (size_t)cur;
                 const float4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2), n3 = __ldg(nd + 3);
+                n_nodes++;
                 float t0, t1;
                 const bool h0 = slab(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, id, ood, best.t, t0);
                 const bool h1 = slab(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, id, ood, best.t, t1);
@@ -134,6 +136,7 @@ __global__ void __launch_bounds__(WF_THREADS, 3) k_wf_trace(const DScene sc, con
             if (cur < 0 && cur != BVH_EMPTY_REF) {
                 const int code = ~cur;
                 const int first = code >> 3, count = (code & 7) + 1;
+                n_prims += count;
                 for (int k = first; k < first + count; ++k) {
                     const float4 A = __ldg(&sc.bvh_tri[3 * k]), E1 = __ldg(&sc.bvh_tri[3 * k + 1]), E2 = __ldg(&sc.bvh_tri[3 * k + 2]);
                     const bool is_sphere = __float_as_int(E1.w) < 0;
@@ -168,6 +171,14 @@ __global__ void __launch_bounds__(WF_THREADS, 3) k_wf_trace(const DScene sc, con
         }
     }
 #undef PTB_WF_POP
+    for (int off = 16; off > 0; off >>= 1) {
+        n_nodes += __shfl_down_sync(0xffffffffu, n_nodes, off);
+        n_prims += __shfl_down_sync(0xffffffffu, n_prims, off);
+    }
+    if (lane == 0 && (n_nodes | n_prims)) {
+        atomicAdd(&counters[1], (unsigned long long)n_nodes);
+        atomicAdd(&counters[2], (unsigned long long)n_prims);
+    }
 }
 
 // material arm of every queued segment; appends the next bounce
@@ -338,7 +349,7 @@ cudaError_t wavefront_render(const DScene &sc, const RenderArgs &a, WfWorkspace 
         (*launches)++;
         for (int b = 0; b < WF_MAX_BOUNCES; ++b) {
             const WfQueue &cur = w.q[b & 1], &nxt = w.q[(b + 1) & 1];
-            k_wf_trace<<<trace_blocks, WF_THREADS, 0, st>>>(sc, cur, w.counters + 2 * b, w.counters + 2 * b + 1);
+            k_wf_trace<<<trace_blocks, WF_THREADS, 0, st>>>(sc, cur, w.counters + 2 * b, w.counters + 2 * b + 1, a.segment_counter);
             k_wf_shade<<<wide_blocks, 256, smem, st>>>(sc, cur, w.counters + 2 * b, nxt, w.counters + 2 * (b + 1), w.slots,
                                                        n_paths, npix, s0, a.seed, a.segment_counter);
             *launches += 2;

@@ -74,6 +74,7 @@ struct ptb_ctx {
     WfWorkspace wf;
     int integrator = 0;             // 0 = auto (wavefront when the scene has a BVH), 1 = megakernel, 2 = wavefront
     double wavefront_paths = 8388608.0;  // ray segments in flight per wavefront batch
+    int wf_refill = 8, wf_descend_min = 12;
     DevBuf<float> fb, scratch_f;
     DevBuf<int> scratch_i;
     DevBuf<int> tile_counter;
@@ -323,7 +324,7 @@ extern "C" int ptb_upload_scene(ptb_ctx *ctx, const ptb_scene_desc *desc) {
     ctx->stats.n_bvh_triangles = ctx->stats.n_bvh_spheres = ctx->stats.n_bvh_nodes = 0;
     {
         std::string berr;
-        cudaError_t e = bvh_build(*desc, in_bvh, prio_base, ctx->bvh, ds, ctx->stream, &bvh_ms, berr);
+        cudaError_t e = bvh_build(*desc, in_bvh, prio_base, ctx->bvh_opt, ctx->bvh, ds, ctx->stream, &bvh_ms, berr);
         if (e != cudaSuccess) return cuda_fail(ctx, e, berr.empty() ? "bvh_build" : berr.c_str());
         ctx->stats.n_bvh_triangles = ctx->bvh.n_tris;
         ctx->stats.n_bvh_spheres = ctx->bvh.n_spheres;
@@ -355,6 +356,10 @@ extern "C" int ptb_set_option(ptb_ctx *ctx, const char *key, double value) {
     const std::string k = key;
     if (k == "bvh_min_tris") ctx->bvh_opt.min_tris = value;
     else if (k == "bvh_min_spheres") ctx->bvh_opt.min_spheres = value;
+    else if (k == "bvh_pad_scale_UNSAFE") ctx->bvh_opt.pad_scale = value;
+    else if (k == "bvh_leaf_max") ctx->bvh_opt.leaf_max = (int)value;
+    else if (k == "wf_refill") ctx->wf_refill = (int)value;
+    else if (k == "wf_descend_min") ctx->wf_descend_min = (int)value;
     else if (k == "integrator") ctx->integrator = (int)value;
     else if (k == "wavefront_paths") ctx->wavefront_paths = std::max(1024.0, value);
     else return fail(ctx, PTB_ERR_ARG, "ptb_set_option: unknown key " + k);
@@ -419,7 +424,7 @@ extern "C" int ptb_render_device(ptb_ctx *ctx, int width, int height, uint64_t s
         a.spp_count = n;
         const bool wavefront = ctx->integrator == 2 || (ctx->integrator == 0 && ctx->ds.bvh_root != BVH_EMPTY_REF);
         if (wavefront) {
-            CU(ctx, wavefront_render(ctx->ds, a, ctx->wf, ctx->sm_count, (size_t)ctx->wavefront_paths, st, &ctx->stats.kernel_launches));
+            CU(ctx, wavefront_render(ctx->ds, a, ctx->wf, ctx->sm_count, (size_t)ctx->wavefront_paths, ctx->wf_refill, ctx->wf_descend_min, st, &ctx->stats.kernel_launches));
         } else {
             CU(ctx, cudaMemsetAsync(ctx->tile_counter.p, 0, sizeof(int), st));
             CU(ctx, launch_render(ctx->ds, a, ctx->sm_count, st));

@@ -10,18 +10,18 @@
 // Mesh hits additionally need the mesh's bounding-sphere gate to pass (mod.rs:267-277); it is evaluated lazily, only
 // when a triangle would become the best hit, and cached per object.
 //
-// Node = 64 bytes = 4 x float4: both children's boxes + two child references.
-//   n0 = (c0.lo.x, c0.lo.y, c0.lo.z, c0.hi.x)   n1 = (c0.hi.y, c0.hi.z, c1.lo.x, c1.lo.y)
-//   n2 = (c1.lo.z, c1.hi.x, c1.hi.y, c1.hi.z)   n3 = (ref0, ref1, -, -) as int bits
+// Node = 128 bytes = 8 x float4, four children in SoA form (one cache line, fetched with seven 16-byte loads):
+//   lo.x[4], lo.y[4], lo.z[4], hi.x[4], hi.y[4], hi.z[4], ref[4] (int bits), unused
+// A node has two to four children, packed from slot 0; an unused slot carries ref = BVH_EMPTY_REF.
 // ref >= 0: inner node index;  ref < 0: leaf, ~ref = (first_prim << 3) | (count - 1), prims contiguous in bvh_tri.
-// Primitive record = 3 x float4 (same as the shared-memory triangle record); a sphere is stored as
-//   (centre | obj), (radius^2, 0, 0 | -1), (0, 0, 0 | prio).
+// Primitive record = (A | obj), (E1 | tri) in bvh_tri (32 bytes, one 256-bit load) + (E2 | prio) in bvh_sph; a sphere is
+// stored as (centre | obj), (radius^2, 0, 0 | -1), (0, 0, 0 | prio).
 #pragma once
 #include "pt_device.cuh"
 
 namespace ptb {
 
-constexpr int BVH_STACK = 64;
+constexpr int BVH_STACK = 96;
 constexpr int BVH_EMPTY_REF = (int)0x80000000;
 
 __device__ __forceinline__ float safe_rcp_dir(float d) {
@@ -42,78 +42,112 @@ __device__ __forceinline__ bool slab(float lx, float ly, float lz, float hx, flo
     return tn <= tf;
 }
 
-// While-while traversal (Aila & Laine 2009): every lane first descends through inner nodes until it holds a leaf (or is
-// done), then all lanes that hold a leaf test its primitives together; the leaf code, which is the longest, then runs
-// with many lanes instead of one or two.  The stack stores the entry distance of a postponed child so that it can be
-// dropped at pop time once a closer hit is known (strictly farther only: ties must still be visited for the prio rule).
-__device__ __forceinline__ void bvh_closest_hit(const DScene &sc, V3 o, V3 d, Hit &best) {
-    int cur = sc.bvh_root;
-    if (cur == BVH_EMPTY_REF) return;
-    const V3 id = mk3(safe_rcp_dir(d.x), safe_rcp_dir(d.y), safe_rcp_dir(d.z));
-    const V3 ood = mk3(o.x * id.x, o.y * id.y, o.z * id.z);
-    int stack_ref[BVH_STACK];
-    float stack_t[BVH_STACK];
-    int sp = 0;
-    int gate_obj = -1;
-    bool gate_pass = false;
+// entry distance of [0, tmax] into the padded box, +inf if it misses
+__device__ __forceinline__ float slab_t(float lx, float ly, float lz, float hx, float hy, float hz, V3 id, V3 ood, float tmax) {
+    float t;
+    return slab(lx, ly, lz, hx, hy, hz, id, ood, tmax, t) ? t : __int_as_float(0x7f800000);
+}
+__device__ __forceinline__ void cswap(float &ta, int &ra, float &tb, int &rb) {
+    const bool s = tb < ta;
+    const float t = s ? tb : ta; tb = s ? ta : tb; ta = t;
+    const int r = s ? rb : ra; rb = s ? ra : rb; ra = r;
+}
+
+// The traversal stack holds (child ref, entry distance) pairs.  PTB_STK(i) names entry i; the includer may define it
+// before including this header's macros (the wavefront trace kernel keeps the first entries in shared memory).
 #define PTB_BVH_POP()                                                    \
     do {                                                                 \
         cur = BVH_EMPTY_REF;                                             \
         while (sp > 0) {                                                 \
             --sp;                                                        \
-            if (stack_t[sp] <= best.t) { cur = stack_ref[sp]; break; }   \
+            const int2 e_ = PTB_STK(sp);                                 \
+            if (__int_as_float(e_.y) <= best.t) { cur = e_.x; break; }   \
         }                                                                \
     } while (0)
+#define PTB_BVH_PUSH(ref_, t_)                                           \
+    do {                                                                 \
+        PTB_STK(sp) = make_int2((ref_), __float_as_int(t_));             \
+        sp++;                                                            \
+    } while (0)
+
+// One step through a four-wide inner node: test the four child boxes, continue with the nearest one that is hit and
+// postpone the others (far to near, so the nearer is popped first) together with their entry distances.
+#define PTB_BVH_NODE_STEP()                                                                                      \
+    do {                                                                                                         \
+        const float4 *nd_ = sc.bvh_nodes + 8 * (size_t)cur;                                                      \
+        const F8 n01_ = ld256(nd_), n23_ = ld256(nd_ + 2), n45_ = ld256(nd_ + 4), n67_ = ld256(nd_ + 6);         \
+        const float4 lx_ = n01_.a, ly_ = n01_.b, lz_ = n23_.a, hx_ = n23_.b, hy_ = n45_.a, hz_ = n45_.b, rf_ = n67_.a; \
+        float t0_ = slab_t(lx_.x, ly_.x, lz_.x, hx_.x, hy_.x, hz_.x, id, ood, best.t);                           \
+        float t1_ = slab_t(lx_.y, ly_.y, lz_.y, hx_.y, hy_.y, hz_.y, id, ood, best.t);                           \
+        float t2_ = slab_t(lx_.z, ly_.z, lz_.z, hx_.z, hy_.z, hz_.z, id, ood, best.t);                           \
+        float t3_ = slab_t(lx_.w, ly_.w, lz_.w, hx_.w, hy_.w, hz_.w, id, ood, best.t);                           \
+        int r0_ = __float_as_int(rf_.x), r1_ = __float_as_int(rf_.y), r2_ = __float_as_int(rf_.z), r3_ = __float_as_int(rf_.w); \
+        const float inf_ = __int_as_float(0x7f800000);                                                           \
+        /* a node has two to four children; the slab test cannot reject an empty slot by itself */               \
+        if (r2_ == BVH_EMPTY_REF) t2_ = inf_;                                                                    \
+        if (r3_ == BVH_EMPTY_REF) t3_ = inf_;                                                                    \
+        cswap(t0_, r0_, t1_, r1_); cswap(t2_, r2_, t3_, r3_); cswap(t0_, r0_, t2_, r2_);                         \
+        cswap(t1_, r1_, t3_, r3_); cswap(t1_, r1_, t2_, r2_);                                                    \
+        if (t0_ < inf_) {                                                                                        \
+            cur = r0_;                                                                                           \
+            if (t3_ < inf_) PTB_BVH_PUSH(r3_, t3_);                                                              \
+            if (t2_ < inf_) PTB_BVH_PUSH(r2_, t2_);                                                              \
+            if (t1_ < inf_) PTB_BVH_PUSH(r1_, t1_);                                                              \
+        } else PTB_BVH_POP();                                                                                    \
+    } while (0)
+
+// Tests the primitives of the leaf `cur` (reference arithmetic, prio tie-break, lazy mesh gate), then pops.
+#define PTB_BVH_LEAF()                                                                                           \
+    do {                                                                                                         \
+        const int code_ = ~cur;                                                                                  \
+        const int first_ = code_ >> 3, count_ = (code_ & 7) + 1;                                                 \
+        for (int k = first_; k < first_ + count_; ++k) {                                                         \
+            const F8 ae_ = ld256(sc.bvh_tri + 2 * (size_t)k);                                                    \
+            const float4 A = ae_.a, E1 = ae_.b, E2 = __ldg(&sc.bvh_sph[k]);                                      \
+            const bool is_sphere = __float_as_int(E1.w) < 0;                                                     \
+            float tt;                                                                                            \
+            if (is_sphere) tt = sphere_t(xyz(A), E1.x, o, d);                                                    \
+            else tt = triangle_t(xyz(A), xyz(E1), xyz(E2), o, d);                                                \
+            const uint32_t prio = (uint32_t)__float_as_int(E2.w);                                                \
+            if (tt > 0.0f && (tt < best.t || (tt == best.t && prio < best.prio))) {                              \
+                bool ok = true;                                                                                  \
+                if (!is_sphere) { /* mesh gate (mod.rs:267-277), evaluated lazily and cached per object */       \
+                    const int obj = __float_as_int(A.w);                                                         \
+                    if (obj != gate_obj) {                                                                       \
+                        const float4 g = __ldg(&sc.obj_gate[obj]);                                               \
+                        gate_pass = sphere_gate(xyz(g), g.w, o, d);                                              \
+                        gate_obj = obj;                                                                          \
+                    }                                                                                            \
+                    ok = gate_pass;                                                                              \
+                }                                                                                                \
+                if (ok) {                                                                                        \
+                    best.t = tt; best.prio = prio;                                                               \
+                    best.ref = REF_BVH_BIT | (is_sphere ? REF_SPHERE_BIT : 0) | k;                               \
+                }                                                                                                \
+            }                                                                                                    \
+        }                                                                                                        \
+        PTB_BVH_POP();                                                                                           \
+    } while (0)
+
+// While-while traversal (Aila & Laine 2009): every lane first descends through inner nodes until it holds a leaf (or is
+// done), then all lanes that hold a leaf test its primitives together.  The stack stores the entry distance of a postponed
+// child so that it can be dropped at pop time once a closer hit is known (strictly farther only: ties must still be
+// visited for the prio rule).
+__device__ __forceinline__ void bvh_closest_hit(const DScene &sc, V3 o, V3 d, Hit &best) {
+    int cur = sc.bvh_root;
+    if (cur == BVH_EMPTY_REF) return;
+    const V3 id = mk3(safe_rcp_dir(d.x), safe_rcp_dir(d.y), safe_rcp_dir(d.z));
+    const V3 ood = mk3(o.x * id.x, o.y * id.y, o.z * id.z);
+    int2 stack_[BVH_STACK];
+#define PTB_STK(i) stack_[i]
+    int sp = 0;
+    int gate_obj = -1;
+    bool gate_pass = false;
     while (cur != BVH_EMPTY_REF) {
-        while (cur >= 0) {
-            const float4 *n = sc.bvh_nodes + 4 * (size_t)cur;
-            const float4 n0 = __ldg(n), n1 = __ldg(n + 1), n2 = __ldg(n + 2), n3 = __ldg(n + 3);
-            float t0, t1;
-            const bool h0 = slab(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, id, ood, best.t, t0);
-            const bool h1 = slab(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, id, ood, best.t, t1);
-            const int r0 = __float_as_int(n3.x), r1 = __float_as_int(n3.y);
-            if (h0 && h1) {
-                const bool first0 = t0 <= t1;
-                cur = first0 ? r0 : r1;
-                stack_ref[sp] = first0 ? r1 : r0;
-                stack_t[sp] = first0 ? t1 : t0;
-                sp++;
-            } else if (h0) cur = r0;
-            else if (h1) cur = r1;
-            else PTB_BVH_POP();
-        }
-        if (cur != BVH_EMPTY_REF) {
-            const int code = ~cur;
-            const int first = code >> 3, count = (code & 7) + 1;
-            for (int k = first; k < first + count; ++k) {
-                const float4 A = __ldg(&sc.bvh_tri[3 * k]), E1 = __ldg(&sc.bvh_tri[3 * k + 1]), E2 = __ldg(&sc.bvh_tri[3 * k + 2]);
-                const bool is_sphere = __float_as_int(E1.w) < 0;
-                float tt;
-                if (is_sphere) tt = sphere_t(xyz(A), E1.x, o, d);
-                else tt = triangle_t(xyz(A), xyz(E1), xyz(E2), o, d);
-                const uint32_t prio = (uint32_t)__float_as_int(E2.w);
-                if (tt > 0.0f && (tt < best.t || (tt == best.t && prio < best.prio))) {
-                    bool ok = true;
-                    if (!is_sphere) {  // mesh gate (mod.rs:267-277), evaluated lazily and cached per object
-                        const int obj = __float_as_int(A.w);
-                        if (obj != gate_obj) {
-                            const float4 g = __ldg(&sc.obj_gate[obj]);
-                            gate_pass = sphere_gate(xyz(g), g.w, o, d);
-                            gate_obj = obj;
-                        }
-                        ok = gate_pass;
-                    }
-                    if (ok) {
-                        best.t = tt;
-                        best.prio = prio;
-                        best.ref = REF_BVH_BIT | (is_sphere ? REF_SPHERE_BIT : 0) | k;
-                    }
-                }
-            }
-            PTB_BVH_POP();
-        }
+        while (cur >= 0) PTB_BVH_NODE_STEP();
+        if (cur != BVH_EMPTY_REF) PTB_BVH_LEAF();
     }
-#undef PTB_BVH_POP
+#undef PTB_STK
 }
 
 }  // namespace ptb

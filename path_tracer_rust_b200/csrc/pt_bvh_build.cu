@@ -1,5 +1,6 @@
 // pt_bvh_build.cu -- LBVH construction on the device (Karras 2012): Morton codes -> radix sort (CUB) -> hierarchy ->
-// bottom-up refit -> collapse small subtrees into multi-primitive leaves -> 64-byte two-child nodes.
+// bottom-up refit -> collapse small subtrees into multi-primitive leaves -> collapse pairs of levels into 128-byte
+// four-child nodes.
 //
 // New with respect to the reference (which is brute force, src/render/mod.rs:631-659 / :554-615).  The hierarchy only
 // selects which primitives are tested; the tests themselves are the reference's arithmetic (pt_device.cuh), and the
@@ -18,7 +19,6 @@ namespace ptb {
 
 namespace {
 
-constexpr int LEAF_MAX = 4;          // primitives per leaf after collapsing (<= 8 by the leaf encoding)
 constexpr float UNIT_ROUNDOFF = 5.9604645e-8f;  // 2^-24
 
 inline float4 f4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
@@ -156,10 +156,10 @@ __global__ void k_refit(const int *__restrict__ idx, const float4 *__restrict__ 
     atomicMax(depth_out, height);
 }
 
-__global__ void k_alive(const int *__restrict__ first, const int *__restrict__ last, int n_inner, int *__restrict__ alive) {
+__global__ void k_alive(const int *__restrict__ first, const int *__restrict__ last, int n_inner, int leaf_max, int *__restrict__ alive) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_inner) return;
-    alive[i] = (last[i] - first[i] + 1) > LEAF_MAX ? 1 : 0;
+    alive[i] = (last[i] - first[i] + 1) > leaf_max ? 1 : 0;
 }
 
 __device__ __forceinline__ void child_ref_and_box(int c, const int *alive, const int *new_index, const int *first, const int *last,
@@ -176,29 +176,54 @@ __device__ __forceinline__ void child_ref_and_box(int c, const int *alive, const
     }
 }
 
-__global__ void k_emit_nodes(int n_inner, const int *__restrict__ alive, const int *__restrict__ new_index,
-                             const int *__restrict__ left, const int *__restrict__ right, const int *__restrict__ first,
-                             const int *__restrict__ last, const int *__restrict__ idx, const float4 *__restrict__ blo,
-                             const float4 *__restrict__ bhi, const float4 *__restrict__ nlo, const float4 *__restrict__ nhi,
-                             float4 *__restrict__ out) {
+// A 4-wide node is a binary node at even depth together with its (alive) children: up to four grandchildren.
+__global__ void k_select4(int n_inner, const int *__restrict__ alive, const int *__restrict__ parent_inner, int *__restrict__ sel) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_inner || !alive[i]) return;
-    int r0, r1;
-    float4 l0, h0, l1, h1;
-    child_ref_and_box(left[i], alive, new_index, first, last, idx, blo, bhi, nlo, nhi, r0, l0, h0);
-    child_ref_and_box(right[i], alive, new_index, first, last, idx, blo, bhi, nlo, nhi, r1, l1, h1);
-    float4 *o = out + 4 * (size_t)new_index[i];
-    o[0] = make_float4(l0.x, l0.y, l0.z, h0.x);
-    o[1] = make_float4(h0.y, h0.z, l1.x, l1.y);
-    o[2] = make_float4(l1.z, h1.x, h1.y, h1.z);
-    o[3] = make_float4(__int_as_float(r0), __int_as_float(r1), 0.f, 0.f);
+    if (i >= n_inner) return;
+    int depth = 0;
+    for (int p = parent_inner[i]; p >= 0; p = parent_inner[p]) depth++;
+    sel[i] = (alive[i] && (depth & 1) == 0) ? 1 : 0;
 }
 
-__global__ void k_gather_prims(const float4 *__restrict__ recs, const int *__restrict__ idx, int n, float4 *__restrict__ out) {
+__global__ void k_emit_nodes4(int n_inner, const int *__restrict__ alive, const int *__restrict__ sel, const int *__restrict__ new4,
+                              const int *__restrict__ left, const int *__restrict__ right, const int *__restrict__ first,
+                              const int *__restrict__ last, const int *__restrict__ idx, const float4 *__restrict__ blo,
+                              const float4 *__restrict__ bhi, const float4 *__restrict__ nlo, const float4 *__restrict__ nhi,
+                              float4 *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_inner || !sel[i]) return;
+    const float inf = __int_as_float(0x7f800000);
+    int ref[4] = {BVH_EMPTY_REF, BVH_EMPTY_REF, BVH_EMPTY_REF, BVH_EMPTY_REF};
+    float4 lo[4], hi[4];
+    for (int k = 0; k < 4; ++k) { lo[k] = make_float4(inf, inf, inf, 0.f); hi[k] = make_float4(-inf, -inf, -inf, 0.f); }
+    int m = 0;
+    const int kids[2] = {left[i], right[i]};
+    for (int c = 0; c < 2; ++c) {
+        const int k = kids[c];
+        if (k >= 0 && alive[k]) {  // expand: its two children become children of the wide node
+            child_ref_and_box(left[k], alive, new4, first, last, idx, blo, bhi, nlo, nhi, ref[m], lo[m], hi[m]); m++;
+            child_ref_and_box(right[k], alive, new4, first, last, idx, blo, bhi, nlo, nhi, ref[m], lo[m], hi[m]); m++;
+        } else {
+            child_ref_and_box(k, alive, new4, first, last, idx, blo, bhi, nlo, nhi, ref[m], lo[m], hi[m]); m++;
+        }
+    }
+    float4 *o = out + 8 * (size_t)new4[i];
+    o[0] = make_float4(lo[0].x, lo[1].x, lo[2].x, lo[3].x);
+    o[1] = make_float4(lo[0].y, lo[1].y, lo[2].y, lo[3].y);
+    o[2] = make_float4(lo[0].z, lo[1].z, lo[2].z, lo[3].z);
+    o[3] = make_float4(hi[0].x, hi[1].x, hi[2].x, hi[3].x);
+    o[4] = make_float4(hi[0].y, hi[1].y, hi[2].y, hi[3].y);
+    o[5] = make_float4(hi[0].z, hi[1].z, hi[2].z, hi[3].z);
+    o[6] = make_float4(__int_as_float(ref[0]), __int_as_float(ref[1]), __int_as_float(ref[2]), __int_as_float(ref[3]));
+    o[7] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+__global__ void k_gather_prims(const float4 *__restrict__ recs, const int *__restrict__ idx, int n, float4 *__restrict__ out_ae,
+                               float4 *__restrict__ out_e2) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int s = idx[i];
-    out[3 * i] = recs[3 * s]; out[3 * i + 1] = recs[3 * s + 1]; out[3 * i + 2] = recs[3 * s + 2];
+    out_ae[2 * i] = recs[3 * s]; out_ae[2 * i + 1] = recs[3 * s + 1]; out_e2[i] = recs[3 * s + 2];
 }
 
 template <typename T>
@@ -251,7 +276,7 @@ void bvh_release(BvhDevice &b) {
         if (e__ != cudaSuccess) { err = #expr; rc = e__; goto done; } \
     } while (0)
 
-cudaError_t bvh_build(const ptb_scene_desc &desc, const std::vector<char> &in_bvh, const std::vector<uint32_t> &prio_base,
+cudaError_t bvh_build(const ptb_scene_desc &desc, const std::vector<char> &in_bvh, const std::vector<uint32_t> &prio_base, const BvhOptions &opt,
                       BvhDevice &out, DScene &ds, cudaStream_t st, double *build_ms, std::string &err) {
     out.n_nodes = out.n_tris = out.n_spheres = 0;
     out.max_depth = 0;
@@ -308,7 +333,7 @@ cudaError_t bvh_build(const ptb_scene_desc &desc, const std::vector<char> &in_bv
             recs.push_back(f4(o.position[0], o.position[1], o.position[2], ibits((int32_t)k)));
             recs.push_back(f4(o.radius * o.radius, 0.f, 0.f, ibits(-1)));  // r^2 as in mod.rs:416
             recs.push_back(f4(0.f, 0.f, 0.f, ubits(prio_base[k])));
-            pads.push_back(sphere_extent(o.radius, D, (float)coord_max));
+            pads.push_back(o.radius + (float)opt.pad_scale * (sphere_extent(o.radius, D, (float)coord_max) - o.radius));
             centroid(o.position[0], o.position[1], o.position[2]);
             n_sph++;
         } else {
@@ -320,7 +345,7 @@ cudaError_t bvh_build(const ptb_scene_desc &desc, const std::vector<char> &in_bv
                 recs.push_back(f4(a.x, a.y, a.z, ibits((int32_t)k)));
                 recs.push_back(f4(e1.x, e1.y, e1.z, ibits((int32_t)j)));
                 recs.push_back(f4(e2.x, e2.y, e2.z, ubits(prio_base[k] + (uint32_t)j)));
-                pads.push_back(triangle_pad(e1, e2, D, (float)coord_max));
+                pads.push_back((float)opt.pad_scale * triangle_pad(e1, e2, D, (float)coord_max));
                 centroid(a.x + (e1.x + e2.x) / 3.0, a.y + (e1.y + e2.y) / 3.0, a.z + (e1.z + e2.z) / 3.0);
                 n_tris++;
             }
@@ -334,7 +359,7 @@ cudaError_t bvh_build(const ptb_scene_desc &desc, const std::vector<char> &in_bv
     float *d_pads = nullptr;
     unsigned long long *d_keys = nullptr, *d_keys2 = nullptr;
     int *d_idx = nullptr, *d_idx2 = nullptr, *d_left = nullptr, *d_right = nullptr, *d_first = nullptr, *d_last = nullptr;
-    int *d_pin = nullptr, *d_pleaf = nullptr, *d_flags = nullptr, *d_alive = nullptr, *d_new = nullptr, *d_depth = nullptr;
+    int *d_pin = nullptr, *d_pleaf = nullptr, *d_flags = nullptr, *d_alive = nullptr, *d_new = nullptr, *d_depth = nullptr, *d_sel = nullptr;
     void *d_tmp = nullptr;
     size_t tmp_bytes = 0, tmp2 = 0;
     const int T = 256, B = (n + T - 1) / T;
@@ -348,7 +373,7 @@ cudaError_t bvh_build(const ptb_scene_desc &desc, const std::vector<char> &in_bv
     BV(dev_alloc(&d_idx, (size_t)n)); BV(dev_alloc(&d_idx2, (size_t)n));
     BV(dev_alloc(&d_left, (size_t)n)); BV(dev_alloc(&d_right, (size_t)n)); BV(dev_alloc(&d_first, (size_t)n)); BV(dev_alloc(&d_last, (size_t)n));
     BV(dev_alloc(&d_pin, (size_t)n)); BV(dev_alloc(&d_pleaf, (size_t)n)); BV(dev_alloc(&d_flags, (size_t)n));
-    BV(dev_alloc(&d_alive, (size_t)n)); BV(dev_alloc(&d_new, (size_t)n)); BV(dev_alloc(&d_depth, 1));
+    BV(dev_alloc(&d_alive, (size_t)n)); BV(dev_alloc(&d_new, (size_t)n)); BV(dev_alloc(&d_depth, 1)); BV(dev_alloc(&d_sel, (size_t)n));
     BV(dev_alloc(&d_nlo, (size_t)n)); BV(dev_alloc(&d_nhi, (size_t)n));
     BV(cudaMemcpyAsync(d_recs, recs.data(), recs.size() * sizeof(float4), cudaMemcpyHostToDevice, st));
     BV(cudaMemcpyAsync(d_pads, pads.data(), pads.size() * sizeof(float), cudaMemcpyHostToDevice, st));
@@ -381,16 +406,19 @@ cudaError_t bvh_build(const ptb_scene_desc &desc, const std::vector<char> &in_bv
         BV(cudaMemsetAsync(d_depth, 0, sizeof(int), st));
         k_refit<<<B, T, 0, st>>>(d_idx2, d_blo, d_bhi, n, d_left, d_right, d_pin, d_pleaf, d_flags, d_nlo, d_nhi, d_depth);
         BV(cudaGetLastError());
-        k_alive<<<(n_inner + T - 1) / T, T, 0, st>>>(d_first, d_last, n_inner, d_alive);
+        k_alive<<<(n_inner + T - 1) / T, T, 0, st>>>(d_first, d_last, n_inner, std::min(8, std::max(1, opt.leaf_max)), d_alive);
         BV(cudaGetLastError());
-        BV(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_alive, d_new, n_inner, st));
+        k_select4<<<(n_inner + T - 1) / T, T, 0, st>>>(n_inner, d_alive, d_pin, d_sel);
+        BV(cudaGetLastError());
+        BV(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_sel, d_new, n_inner, st));
         int last_alive = 0, last_new = 0;
-        BV(cudaMemcpyAsync(&last_alive, d_alive + (n_inner - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+        BV(cudaMemcpyAsync(&last_alive, d_sel + (n_inner - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
         BV(cudaMemcpyAsync(&last_new, d_new + (n_inner - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
         BV(cudaMemcpyAsync(&h_depth, d_depth, sizeof(int), cudaMemcpyDeviceToHost, st));
         BV(cudaStreamSynchronize(st));
         n_alive = last_alive + last_new;
-        if (h_depth > BVH_STACK) { err = "BVH deeper than the traversal stack"; rc = cudaErrorInvalidValue; goto done; }
+        // a four-wide step pushes at most three entries per pair of binary levels
+        if (3 * (h_depth / 2 + 1) > BVH_STACK) { err = "BVH deeper than the traversal stack"; rc = cudaErrorInvalidValue; goto done; }
     } else {
         BV(cudaMemcpyAsync(d_idx2, d_idx, 0, cudaMemcpyDeviceToDevice, st));
         int zero = 0;
@@ -400,17 +428,17 @@ cudaError_t bvh_build(const ptb_scene_desc &desc, const std::vector<char> &in_bv
         if (out.cap_nodes < (size_t)n_alive) {
             if (out.nodes) cudaFree(out.nodes);
             out.nodes = nullptr; out.cap_nodes = 0;
-            BV(dev_alloc(&out.nodes, 4 * (size_t)n_alive));
+            BV(dev_alloc(&out.nodes, 8 * (size_t)n_alive));
             out.cap_nodes = (size_t)n_alive;
         }
-        k_emit_nodes<<<(n_inner + T - 1) / T, T, 0, st>>>(n_inner, d_alive, d_new, d_left, d_right, d_first, d_last, d_idx2, d_blo,
-                                                           d_bhi, d_nlo, d_nhi, out.nodes);
+        k_emit_nodes4<<<(n_inner + T - 1) / T, T, 0, st>>>(n_inner, d_alive, d_sel, d_new, d_left, d_right, d_first, d_last, d_idx2, d_blo,
+                                                            d_bhi, d_nlo, d_nhi, out.nodes);
         BV(cudaGetLastError());
         ds.bvh_root = 0;  // Karras' internal node 0 is the root and is always alive here
     } else {
         ds.bvh_root = ~((0 << 3) | (n - 1));  // the whole set fits one leaf
     }
-    k_gather_prims<<<B, T, 0, st>>>(d_recs, d_idx2, n, out.tris);
+    k_gather_prims<<<B, T, 0, st>>>(d_recs, d_idx2, n, out.tris, out.tris + 2 * (size_t)n);
     BV(cudaGetLastError());
     BV(cudaEventRecord(ev1, st));
     BV(cudaStreamSynchronize(st));
@@ -420,12 +448,12 @@ cudaError_t bvh_build(const ptb_scene_desc &desc, const std::vector<char> &in_bv
         if (build_ms) *build_ms = ms;
     }
     out.n_nodes = (unsigned)n_alive; out.n_tris = n_tris; out.n_spheres = n_sph; out.max_depth = h_depth;
-    ds.bvh_nodes = out.nodes; ds.bvh_tri = out.tris; ds.n_bvh_nodes = n_alive;
+    ds.bvh_nodes = out.nodes; ds.bvh_tri = out.tris; ds.bvh_sph = out.tris + 2 * (size_t)n; ds.n_bvh_nodes = n_alive;
 
 done:
     cudaFree(d_recs); cudaFree(d_pads); cudaFree(d_blo); cudaFree(d_bhi); cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_idx);
     cudaFree(d_idx2); cudaFree(d_left); cudaFree(d_right); cudaFree(d_first); cudaFree(d_last); cudaFree(d_pin); cudaFree(d_pleaf);
-    cudaFree(d_flags); cudaFree(d_alive); cudaFree(d_new); cudaFree(d_depth); cudaFree(d_nlo); cudaFree(d_nhi); cudaFree(d_tmp);
+    cudaFree(d_flags); cudaFree(d_sel); cudaFree(d_alive); cudaFree(d_new); cudaFree(d_depth); cudaFree(d_nlo); cudaFree(d_nhi); cudaFree(d_tmp);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (rc != cudaSuccess) ds.bvh_root = BVH_EMPTY_REF;

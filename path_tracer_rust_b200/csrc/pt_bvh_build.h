@@ -12,8 +12,8 @@ namespace ptb {
 
 
 struct BvhDevice {
-    float4 *nodes = nullptr;  // 4 x float4 per node
-    float4 *tris = nullptr;   // 3 x float4 per primitive (triangles and spheres), leaf order
+    float4 *nodes = nullptr;  // 8 x float4 per four-wide node
+    float4 *tris = nullptr;   // [2n] (A, E1) pairs then [n] E2, leaf order (triangles and spheres)
     unsigned n_nodes = 0, n_tris = 0, n_spheres = 0;
     int max_depth = 0;
     size_t cap_nodes = 0, cap_tris = 0;
@@ -23,10 +23,12 @@ struct BvhDevice {
 struct BvhOptions {
     double min_tris = 24;     // meshes with fewer triangles stay in the lock-step shared-memory list
     double min_spheres = 48;  // scenes with fewer spheres keep them in the shared-memory list
+    int leaf_max = 2;         // primitives per leaf after collapsing small subtrees (1..8); measured best on B200
+    double pad_scale = 1.0;   // EXPERIMENTS ONLY: scales the conservative box padding; anything below 1 voids the parity guarantee
 };
 void choose_bvh_objects(const ptb_scene_desc &desc, size_t max_smem_bytes, const BvhOptions &opt, std::vector<char> &in_bvh);
 // builds the BVH over the chosen objects on the device and fills the bvh_* fields of `ds`
-cudaError_t bvh_build(const ptb_scene_desc &desc, const std::vector<char> &in_bvh, const std::vector<uint32_t> &prio_base,
+cudaError_t bvh_build(const ptb_scene_desc &desc, const std::vector<char> &in_bvh, const std::vector<uint32_t> &prio_base, const BvhOptions &opt,
                       BvhDevice &out, DScene &ds, cudaStream_t st, double *build_ms, std::string &err);
 void bvh_release(BvhDevice &b);
 

@@ -23,8 +23,8 @@ namespace ptb {
 namespace {
 
 constexpr int WF_THREADS = 256;
-constexpr int WF_REFILL = 8;        // idle lanes that trigger a refill of the warp
-constexpr int WF_DESCEND_MIN = 12;  // leave the inner-node loop when fewer lanes than this are still descending
+constexpr int WF_CHUNK = 512;  // rays a warp takes from the queue per global atomic
+constexpr int WF_SSTACK = 12;  // traversal-stack entries per lane kept in shared memory (deeper entries go to local memory)
 
 __device__ __forceinline__ void store_loose_hit(const WfQueue &q, size_t j, const float4 *s_obj, const float4 *s_tri, int n_loose,
                                                 V3 o, V3 d, unsigned amask) {
@@ -66,46 +66,49 @@ __global__ void __launch_bounds__(256) k_wf_generate(const DScene sc, int W, int
 
 // closest hit of every queued segment
 __global__ void __launch_bounds__(WF_THREADS, 3) k_wf_trace(const DScene sc, const WfQueue q, const int *__restrict__ n_rays_ptr,
-                                                             int *__restrict__ fetch_ptr, unsigned long long *__restrict__ counters) {
+                                                             int *__restrict__ fetch_ptr, unsigned long long *__restrict__ counters,
+                                                             const int wf_refill, const int wf_descend_min) {
     const int n = *n_rays_ptr;
     unsigned n_nodes = 0, n_prims = 0;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
 
     bool busy = false, exhausted = false;
+    int w_next = 0, w_end = 0;  // warp-uniform
     int ray_idx = 0;
     V3 o = mk3(0.f, 0.f, 0.f), d = mk3(0.f, 0.f, 1.f), id = mk3(1.f, 1.f, 1.f), ood = mk3(0.f, 0.f, 0.f);
     Hit best;
     best.t = 0.f; best.prio = PRIO_NONE; best.ref = REF_NONE;
     int cur = BVH_EMPTY_REF, sp = 0, gate_obj = -1;
     bool gate_pass = false;
-    int stack_ref[BVH_STACK];
-    float stack_t[BVH_STACK];
-
-#define PTB_WF_POP()                                                     \
-    do {                                                                 \
-        cur = BVH_EMPTY_REF;                                             \
-        while (sp > 0) {                                                 \
-            --sp;                                                        \
-            if (stack_t[sp] <= best.t) { cur = stack_ref[sp]; break; }   \
-        }                                                                \
-    } while (0)
+    // traversal stack: the hot top of it lives in shared memory (entry-major, conflict-free 8-byte accesses), so a pop
+    // costs a fixed ~30 cycles instead of a local-memory load that competes with node data for the L1
+    __shared__ int2 s_stack[WF_SSTACK * WF_THREADS];
+    int2 l_stack[BVH_STACK - WF_SSTACK];
+#define PTB_STK(i) (*((i) < WF_SSTACK ? &s_stack[(i) * WF_THREADS + threadIdx.x] : &l_stack[(i) - WF_SSTACK]))
 
     for (;;) {
         const unsigned busy_mask = __ballot_sync(0xffffffffu, busy);
         const int n_idle = 32 - __popc(busy_mask);
-        if (!exhausted && (n_idle >= WF_REFILL || busy_mask == 0u)) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(fetch_ptr, n_idle);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            const int idx = base + __popc(~busy_mask & lt_mask);
-            const bool got = !busy && idx < n;
-            if (base + n_idle >= n) exhausted = true;
+        if (!exhausted && (n_idle >= wf_refill || busy_mask == 0u)) {
+            // the warp owns a private chunk [w_next, w_end) of the queue and only touches the global cursor when it runs dry:
+            // one same-address atomic per WF_CHUNK rays instead of one per refill
+            if (w_next >= w_end) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(fetch_ptr, WF_CHUNK);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                w_next = base;
+                w_end = min(base + WF_CHUNK, n);
+                if (base >= n) exhausted = true;
+            }
+            const int idx = w_next + __popc(~busy_mask & lt_mask);
+            const bool got = !busy && idx < w_end;
+            w_next = min(w_next + n_idle, w_end);
             if (got) {
-                const float4 qo = __ldg(&q.o[idx]), qd = __ldg(&q.d[idx]);
+                const float4 qo = __ldcs(&q.o[idx]), qd = __ldcs(&q.d[idx]);  // streaming: keep the L2 for the BVH
                 o = mk3(qo.x, qo.y, qo.z); d = mk3(qd.x, qd.y, qd.z);
                 ray_idx = idx;
-                best.t = q.hit_t[idx]; best.ref = q.hit_ref[idx]; best.prio = q.hit_prio[idx];
+                best.t = __ldcs(&q.hit_t[idx]); best.ref = __ldcs(&q.hit_ref[idx]); best.prio = __ldcs(&q.hit_prio[idx]);
                 id = mk3(safe_rcp_dir(d.x), safe_rcp_dir(d.y), safe_rcp_dir(d.z));
                 ood = mk3(o.x * id.x, o.y * id.y, o.z * id.z);
                 cur = sc.bvh_root; sp = 0; gate_obj = -1;
@@ -115,62 +118,22 @@ __global__ void __launch_bounds__(WF_THREADS, 3) k_wf_trace(const DScene sc, con
         if (__ballot_sync(0xffffffffu, busy) == 0u) break;
         if (busy) {
             while (cur >= 0) {  // descend until this lane holds a leaf or is done
-                const float4 *nd = sc.bvh_nodes + 4 * (size_t)cur;
-                const float4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2), n3 = __ldg(nd + 3);
+                PTB_BVH_NODE_STEP();
                 n_nodes++;
-                float t0, t1;
-                const bool h0 = slab(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, id, ood, best.t, t0);
-                const bool h1 = slab(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, id, ood, best.t, t1);
-                const int r0 = __float_as_int(n3.x), r1 = __float_as_int(n3.y);
-                if (h0 && h1) {
-                    const bool first0 = t0 <= t1;
-                    cur = first0 ? r0 : r1;
-                    stack_ref[sp] = first0 ? r1 : r0;
-                    stack_t[sp] = first0 ? t1 : t0;
-                    sp++;
-                } else if (h0) cur = r0;
-                else if (h1) cur = r1;
-                else PTB_WF_POP();
-                if (__popc(__activemask()) < WF_DESCEND_MIN) break;  // let the lanes that hold a leaf get on with it
+                if (__popc(__activemask()) < wf_descend_min) break;  // let the lanes that hold a leaf get on with it
             }
             if (cur < 0 && cur != BVH_EMPTY_REF) {
-                const int code = ~cur;
-                const int first = code >> 3, count = (code & 7) + 1;
-                n_prims += count;
-                for (int k = first; k < first + count; ++k) {
-                    const float4 A = __ldg(&sc.bvh_tri[3 * k]), E1 = __ldg(&sc.bvh_tri[3 * k + 1]), E2 = __ldg(&sc.bvh_tri[3 * k + 2]);
-                    const bool is_sphere = __float_as_int(E1.w) < 0;
-                    float tt;
-                    if (is_sphere) tt = sphere_t(xyz(A), E1.x, o, d);
-                    else tt = triangle_t(xyz(A), xyz(E1), xyz(E2), o, d);
-                    const uint32_t prio = (uint32_t)__float_as_int(E2.w);
-                    if (tt > 0.0f && (tt < best.t || (tt == best.t && prio < best.prio))) {
-                        bool ok = true;
-                        if (!is_sphere) {  // mesh gate (mod.rs:267-277), lazily, cached per object
-                            const int obj = __float_as_int(A.w);
-                            if (obj != gate_obj) {
-                                const float4 g = __ldg(&sc.obj_gate[obj]);
-                                gate_pass = sphere_gate(xyz(g), g.w, o, d);
-                                gate_obj = obj;
-                            }
-                            ok = gate_pass;
-                        }
-                        if (ok) {
-                            best.t = tt; best.prio = prio;
-                            best.ref = REF_BVH_BIT | (is_sphere ? REF_SPHERE_BIT : 0) | k;
-                        }
-                    }
-                }
-                PTB_WF_POP();
+                n_prims += ((~cur) & 7) + 1;
+                PTB_BVH_LEAF();
             }
             if (cur == BVH_EMPTY_REF) {
-                q.hit_t[ray_idx] = best.t;
-                q.hit_ref[ray_idx] = best.ref;
+                __stcs(&q.hit_t[ray_idx], best.t);
+                __stcs(&q.hit_ref[ray_idx], best.ref);
                 busy = false;
             }
         }
     }
-#undef PTB_WF_POP
+#undef PTB_STK
     for (int off = 16; off > 0; off >>= 1) {
         n_nodes += __shfl_down_sync(0xffffffffu, n_nodes, off);
         n_prims += __shfl_down_sync(0xffffffffu, n_prims, off);
@@ -317,7 +280,8 @@ static cudaError_t wf_reserve(WfWorkspace &w, size_t n_paths) {
 }
 
 // renders samples [a.spp_begin, a.spp_begin + a.spp_count) of every pixel into a.sum_rgb; returns the number of kernels launched
-cudaError_t wavefront_render(const DScene &sc, const RenderArgs &a, WfWorkspace &w, int sm_count, size_t target_paths, cudaStream_t st,
+cudaError_t wavefront_render(const DScene &sc, const RenderArgs &a, WfWorkspace &w, int sm_count, size_t target_paths, int refill,
+                             int descend_min, cudaStream_t st,
                              unsigned *launches) {
     const unsigned npix = (unsigned)a.width * (unsigned)a.height;
     unsigned K = (unsigned)std::max<size_t>(1, target_paths / npix);
@@ -349,7 +313,7 @@ cudaError_t wavefront_render(const DScene &sc, const RenderArgs &a, WfWorkspace 
         (*launches)++;
         for (int b = 0; b < WF_MAX_BOUNCES; ++b) {
             const WfQueue &cur = w.q[b & 1], &nxt = w.q[(b + 1) & 1];
-            k_wf_trace<<<trace_blocks, WF_THREADS, 0, st>>>(sc, cur, w.counters + 2 * b, w.counters + 2 * b + 1, a.segment_counter);
+            k_wf_trace<<<trace_blocks, WF_THREADS, 0, st>>>(sc, cur, w.counters + 2 * b, w.counters + 2 * b + 1, a.segment_counter, refill, descend_min);
             k_wf_shade<<<wide_blocks, 256, smem, st>>>(sc, cur, w.counters + 2 * b, nxt, w.counters + 2 * (b + 1), w.slots,
                                                        n_paths, npix, s0, a.seed, a.segment_counter);
             *launches += 2;

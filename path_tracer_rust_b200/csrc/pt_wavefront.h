@@ -31,7 +31,8 @@ struct WfWorkspace {
 };
 
 void wf_release(WfWorkspace &w);
-cudaError_t wavefront_render(const DScene &sc, const RenderArgs &a, WfWorkspace &w, int sm_count, size_t target_paths, cudaStream_t st,
+cudaError_t wavefront_render(const DScene &sc, const RenderArgs &a, WfWorkspace &w, int sm_count, size_t target_paths, int refill,
+                             int descend_min, cudaStream_t st,
                              unsigned *launches);
 
 }  // namespace ptb

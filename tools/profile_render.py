@@ -15,6 +15,9 @@ H = int(sys.argv[3]) if len(sys.argv) > 3 else 1080
 spp = int(sys.argv[4]) if len(sys.argv) > 4 else 32
 reps = int(sys.argv[5]) if len(sys.argv) > 5 else 3
 be = P.Backend(0)
+for kv in os.environ.get('PTB_OPTS', '').split(','):
+    if '=' in kv:
+        be.set_option(kv.split('=')[0], float(kv.split('=')[1]))
 be.upload_scene(P.Scene.load(scene))
 for i in range(reps):
     t0 = time.perf_counter()

@@ -30,6 +30,11 @@ t1 = time.perf_counter()
 sc = P.Scene.load(path, base_dir=out)
 t2 = time.perf_counter()
 be = P.Backend(0)
+if os.environ.get('PAD_SCALE'):
+    be.set_option('bvh_pad_scale_UNSAFE', float(os.environ['PAD_SCALE']))
+for kv in os.environ.get('PTB_OPTS', '').split(','):
+    if '=' in kv:
+        be.set_option(kv.split('=')[0], float(kv.split('=')[1]))
 be.upload_scene(sc)
 t3 = time.perf_counter()
 st = be.stats()
@@ -40,7 +45,8 @@ for i in range(2):
     be.render(W, H, spp, seed=i, out_kind=A.PTB_OUT_SUM)
     s = be.stats()
     print(f"render {W}x{H}x{spp}: {s['render_ms']:.1f} ms, {s['samples']/s['render_ms']*1e-3:.1f} Mpaths/s, "
-          f"{s['segments']/s['render_ms']*1e-3:.1f} Mseg/s, {s['segments']/s['samples']:.2f} seg/sample", flush=True)
+          f"{s['segments']/s['render_ms']*1e-3:.1f} Mseg/s, {s['segments']/s['samples']:.2f} seg/sample, "
+          f"{s['bvh_nodes_visited']/max(s['segments'],1):.1f} nodes/seg, {s['bvh_prims_tested']/max(s['segments'],1):.1f} prims/seg", flush=True)
 if os.environ.get("SYN_ORACLE", "1") == "1":
     import oracle_lib as O
     osc = O.OracleScene(path, out)

@@ -304,6 +304,12 @@ def main():
         seg_per_gpu = seg_total / max(world, 1) / args.steps
         kern_s = kernel_ms_last * 1e-3
         achieved = seg_per_gpu * flops_per_seg / kern_s * 1e-12 if kern_s > 0 else None
+        traffic, ncu_note = None, None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath) and not reduced:
+            tj = json.load(open(tpath)).get(args.workload)
+            if tj:
+                traffic, ncu_note = tj["dram_bytes_per_launch"], {k: tj[k] for k in ("kernel", "launch", "algorithmic_bytes_per_launch", "ncu", "source")}
         line = {
             "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / max(args.steps, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -318,7 +324,7 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "fp32_issue", "achieved": achieved, "peak": fp32_peak, "unit": "Tlane-op/s",
-                         "frac": (achieved / fp32_peak) if achieved else None, "traffic": None,
+                         "frac": (achieved / fp32_peak) if achieved else None, "traffic": traffic, "traffic_detail": ncu_note,
                          "kernel": dominant, "flops_per_segment": flops_per_seg, "tests_per_segment": tps, "kernel_ms": kernel_ms_last,
                          "peak_source": f"SMs({sms}) x 128 lanes x sm_max_mhz({peaks['sm_max_mhz']}) from MEASURED_PEAKS.json ({peaks['source']}); "
                                         "no tensor or HBM bound applies: scene and path state live in shared memory / registers"},

@@ -301,3 +301,24 @@ def test_wavefront_equals_megakernel_equals_oracle(sid, W, H, spp, paths):
     finally:
         wf.close()
         mk.close()
+
+
+def test_render_cli_writes_reference_ppm(tmp_path):
+    """The resurrected `render <spp> <res_y> <scene>` command (cmd_render.rs:17-44): its PPM must equal, byte for byte, the PPM the
+    oracle writes for the same seed (P3, two comment lines, reversed pixel order, gamma 2.2 -> u8; mod.rs:1042-1076)."""
+    import os, subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "path_tracer_rust_b200", "render")
+    out = tmp_path / "cli.ppm"
+    r = subprocess.run([exe, "6", "40", "cornell", "--seed", "13", "--out", str(out)], cwd=ROOT, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Rendering scene cornell (11 objects), 6 samples per pixel, 60x40 resolution" in r.stdout
+    osc = O.OracleScene(scene_path("cornell"))
+    fb, _ = osc.render_sum(60, 40, 6, seed=13)
+    mean = O.resolve(fb, 6)
+    ref = tmp_path / "ref.ppm"
+    O.lib().pto_write_ppm(str(ref).encode(), O._fp(np.ascontiguousarray(mean)), 60, 40, 6, b"cornell", 0)
+    strip = lambda t: [l for l in t.split("\n") if not l.startswith("# rendering time")]
+    assert strip(out.read_text()) == strip(ref.read_text())
+    bad = subprocess.run([exe, "6", "40", "no-such-scene"], cwd=ROOT, capture_output=True, text=True, timeout=60)
+    assert bad.returncode == 1 and "cannot open" in bad.stderr

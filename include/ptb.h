@@ -90,6 +90,11 @@ typedef struct ptb_stats {
 /* ---- host-side scene I/O: SceneDescriptor::load + to_data (mod.rs:92-110, 304-318), load_off.rs:8-85 ---- */
 int ptb_scene_load_json(const char *json_path, const char *base_dir, ptb_scene **out, char *err, size_t errlen);
 const ptb_scene_desc *ptb_scene_get_desc(const ptb_scene *scene);
+/* SceneData::to_descriptor + SceneDescriptor::save (mod.rs:112-150): writes serde_json::to_string_pretty's exact layout
+ * (MeshFile objects keep their path + scale, inline meshes their serialised bounding sphere and box). */
+int ptb_scene_save_json(const ptb_scene *scene, const char *json_path);
+/* the GUI edits the camera and saves the scene (viewport_tab.rs); same here */
+int ptb_scene_set_camera(ptb_scene *scene, const ptb_camera *camera);
 const char *ptb_scene_id(const ptb_scene *scene);
 void ptb_scene_free(ptb_scene *scene);
 

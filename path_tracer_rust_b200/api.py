@@ -66,7 +66,7 @@ _lib = None
 _lib_lock = threading.Lock()
 
 # every symbol include/ptb.h declares
-ABI_SYMBOLS = ["ptb_scene_load_json", "ptb_scene_get_desc", "ptb_scene_id", "ptb_scene_free", "ptb_abi_version",
+ABI_SYMBOLS = ["ptb_scene_load_json", "ptb_scene_save_json", "ptb_scene_set_camera", "ptb_scene_get_desc", "ptb_scene_id", "ptb_scene_free", "ptb_abi_version",
                "ptb_device_count", "ptb_create", "ptb_destroy", "ptb_last_error", "ptb_upload_scene", "ptb_get_stats", "ptb_set_option", "ptb_selftest",
                "ptb_render", "ptb_render_device", "ptb_resolve_device", "ptb_primary_hits", "ptb_intersect",
                "ptb_to_int_with_gamma_correction", "ptb_write_ppm", "ptb_hash_pixels"]
@@ -85,6 +85,8 @@ def load_library():
         L = C.CDLL(path)
         fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int32)
         L.ptb_scene_load_json.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p), C.c_char_p, C.c_size_t]
+        L.ptb_scene_save_json.argtypes = [C.c_void_p, C.c_char_p]
+        L.ptb_scene_set_camera.argtypes = [C.c_void_p, C.POINTER(_Camera)]
         L.ptb_scene_get_desc.restype = C.POINTER(_SceneDesc)
         L.ptb_scene_get_desc.argtypes = [C.c_void_p]
         L.ptb_scene_id.restype = C.c_char_p
@@ -183,6 +185,24 @@ class Scene:
         desc.camera.sensor_width = camera.get("sensor_width", 0.036)
         desc.camera.aspect_ratio = camera.get("aspect_ratio", 1.5)
         return cls(desc=C.pointer(desc), keepalive=(objs, tris, desc), scene_id=scene_id)
+
+    def save(self, path: str):
+        """SceneDescriptor::save (mod.rs:112-117) for a scene that came from Scene.load."""
+        if not self._h:
+            raise BackendError(-5, "only scenes loaded from JSON can be saved")
+        rc = load_library().ptb_scene_save_json(self._h, path.encode())
+        if rc != PTB_OK:
+            raise BackendError(rc, "ptb_scene_save_json failed")
+
+    def set_camera(self, position, direction, focal_length=0.035, sensor_width=0.036, aspect_ratio=1.5):
+        if not self._h:
+            raise BackendError(-5, "only scenes loaded from JSON can be edited")
+        cam = _Camera()
+        for k in range(3):
+            cam.position[k] = position[k]
+            cam.direction[k] = direction[k]
+        cam.focal_length, cam.sensor_width, cam.aspect_ratio = focal_length, sensor_width, aspect_ratio
+        load_library().ptb_scene_set_camera(self._h, C.byref(cam))
 
     @property
     def id(self) -> str:

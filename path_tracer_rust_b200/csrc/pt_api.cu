@@ -128,6 +128,21 @@ extern "C" int ptb_scene_load_json(const char *json_path, const char *base_dir, 
         return fail(nullptr, PTB_ERR_PARSE, e.what());
     }
 }
+extern "C" int ptb_scene_save_json(const ptb_scene *scene, const char *json_path) {
+    if (!scene || !json_path) return fail(nullptr, PTB_ERR_ARG, "ptb_scene_save_json: null argument");
+    try {
+        save_scene_json(scene->host, json_path);
+        return PTB_OK;
+    } catch (const SceneError &e) {
+        return fail(nullptr, e.code, e.what());
+    }
+}
+extern "C" int ptb_scene_set_camera(ptb_scene *scene, const ptb_camera *camera) {
+    if (!scene || !camera) return fail(nullptr, PTB_ERR_ARG, "ptb_scene_set_camera: null argument");
+    scene->host.camera = *camera;
+    scene->host.refresh_desc();
+    return PTB_OK;
+}
 extern "C" const ptb_scene_desc *ptb_scene_get_desc(const ptb_scene *scene) { return scene ? &scene->host.desc : nullptr; }
 extern "C" const char *ptb_scene_id(const ptb_scene *scene) { return scene ? scene->host.id.c_str() : ""; }
 extern "C" void ptb_scene_free(ptb_scene *scene) { delete scene; }

@@ -316,6 +316,7 @@ HostScene load_scene_json(const std::string &json_path, const std::string &base_
             const std::string &variant = ty->members[0].first;
             const Json &body = ty->members[0].second;
             o.tri_begin = sc.triangles.size();
+            ObjectSource src;
             if (variant == "Sphere") {
                 o.kind = PTB_OBJ_SPHERE;
                 o.radius = need_f32(body.get("radius"), "radius");
@@ -326,6 +327,7 @@ HostScene load_scene_json(const std::string &json_path, const std::string &base_
                 const float scale = need_f32(body.get("scale"), "scale");
                 std::string full = p->text;
                 if (!full.empty() && full[0] != '/' && !base_dir.empty()) full = base_dir + "/" + full;
+                src.variant = 1; src.path = p->text; src.scale = scale;
                 load_off(full, scale, sc.triangles);
                 o.tri_count = sc.triangles.size() - o.tri_begin;
                 mesh_bounding_sphere(sc.triangles.data() + o.tri_begin, o.tri_count, o.bs_position, &o.bs_radius);
@@ -346,17 +348,173 @@ HostScene load_scene_json(const std::string &json_path, const std::string &base_
                 if (!bs) throw SceneError(PTB_ERR_PARSE, "missing field `bounding_sphere`");
                 need_vec3(bs->get("position"), "position", o.bs_position);
                 o.bs_radius = need_f32(bs->get("radius"), "radius");
-                if (!body.get("bounding_box")) throw SceneError(PTB_ERR_PARSE, "missing field `bounding_box`");
+                const Json *bb = body.get("bounding_box");
+                if (!bb || bb->kind != Json::Array) throw SceneError(PTB_ERR_PARSE, "missing field `bounding_box`");
+                src.variant = 2;
+                for (const Json &jt : bb->elems) {
+                    ptb_triangle t;
+                    need_vec3(jt.get("a"), "a", t.a);
+                    need_vec3(jt.get("b"), "b", t.b);
+                    need_vec3(jt.get("c"), "c", t.c);
+                    src.bounding_box.push_back(t);
+                }
             } else {
                 throw SceneError(PTB_ERR_PARSE, "unknown variant `" + variant + "`, expected one of `Sphere`, `MeshFile`, `Mesh`");
             }
             sc.objects.push_back(o);
+            sc.sources.push_back(std::move(src));
         } catch (const SceneError &e) {
             throw SceneError(e.code, "objects[" + std::to_string(i) + "]: " + e.what());
         }
     }
     sc.refresh_desc();
     return sc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// write-back: SceneData::to_descriptor + SceneDescriptor::save (mod.rs:112-150)
+// ------------------------------------------------------------------------------------------------
+// serde_json prints an f32 with ryu: the shortest decimal that parses back to the same f32, plain notation while the decimal
+// point stays within the digits' reach (ryu's pretty printer), exponent notation otherwise, always with a fraction ("1.0").
+std::string format_f32(float v) {
+    if (std::isnan(v) || std::isinf(v)) return "null";  // serde_json writes non-finite floats as null
+    if (v == 0.0f) return std::signbit(v) ? "-0.0" : "0.0";
+    char buf[64];
+    int prec = 1;
+    for (; prec <= 9; ++prec) {
+        std::snprintf(buf, sizeof buf, "%.*e", prec - 1, static_cast<double>(v));
+        if (std::strtof(buf, nullptr) == v) break;
+    }
+    std::string digits;
+    bool neg = false;
+    int exp10 = 0;
+    {
+        const char *p = buf;
+        if (*p == '-') { neg = true; ++p; }
+        for (; *p && *p != 'e'; ++p)
+            if (*p != '.') digits += *p;
+        exp10 = std::atoi(p + 1);
+    }
+    while (digits.size() > 1 && digits.back() == '0') digits.pop_back();
+    const int len = static_cast<int>(digits.size());
+    const int k = exp10 - (len - 1);  // value = digits * 10^k
+    const int kk = len + k;           // position of the decimal point
+    std::string out = neg ? "-" : "";
+    if (0 <= k && kk <= 16) {
+        out += digits + std::string(static_cast<size_t>(k), '0') + ".0";
+    } else if (0 < kk && kk <= 16) {
+        out += digits.substr(0, static_cast<size_t>(kk)) + "." + digits.substr(static_cast<size_t>(kk));
+    } else if (-5 < kk && kk <= 0) {
+        out += "0." + std::string(static_cast<size_t>(-kk), '0') + digits;
+    } else {
+        out += digits.substr(0, 1);
+        if (len > 1) out += "." + digits.substr(1);
+        out += "e" + std::to_string(kk - 1);
+    }
+    return out;
+}
+
+namespace {
+struct PrettyWriter {
+    std::string out;
+    int depth = 0;
+    void nl() { out += "\n"; out.append(static_cast<size_t>(depth) * 2, ' '); }
+    void vec3(const float *v) {
+        out += "[";
+        ++depth;
+        for (int i = 0; i < 3; ++i) { nl(); out += format_f32(v[i]); if (i < 2) out += ","; }
+        --depth; nl();
+        out += "]";
+    }
+    void str(const std::string &s) {
+        out += '"';
+        for (char c : s) {
+            if (c == '"' || c == '\\') { out += '\\'; out += c; }
+            else if (c == '\n') out += "\\n";
+            else if (c == '\t') out += "\\t";
+            else out += c;
+        }
+        out += '"';
+    }
+    void triangle(const ptb_triangle &t) {
+        out += "{"; ++depth;
+        nl(); out += "\"a\": "; vec3(t.a); out += ",";
+        nl(); out += "\"b\": "; vec3(t.b); out += ",";
+        nl(); out += "\"c\": "; vec3(t.c);
+        --depth; nl(); out += "}";
+    }
+    void triangles(const ptb_triangle *t, size_t n) {
+        if (n == 0) { out += "[]"; return; }
+        out += "["; ++depth;
+        for (size_t i = 0; i < n; ++i) { nl(); triangle(t[i]); if (i + 1 < n) out += ","; }
+        --depth; nl(); out += "]";
+    }
+};
+}  // namespace
+
+std::string scene_to_json(const HostScene &sc) {
+    static const char *kRefl[] = {"Diffuse", "Specular", "Refract"};
+    PrettyWriter w;
+    w.out += "{"; ++w.depth;
+    w.nl(); w.out += "\"id\": "; w.str(sc.id); w.out += ",";
+    w.nl(); w.out += "\"objects\": ";
+    if (sc.objects.empty()) w.out += "[]";
+    else {
+        w.out += "["; ++w.depth;
+        for (size_t i = 0; i < sc.objects.size(); ++i) {
+            const ptb_object &o = sc.objects[i];
+            const ObjectSource src = i < sc.sources.size() ? sc.sources[i] : ObjectSource{};
+            w.nl(); w.out += "{"; ++w.depth;
+            w.nl(); w.out += "\"type_\": {"; ++w.depth;
+            if (o.kind == PTB_OBJ_SPHERE) {
+                w.nl(); w.out += "\"Sphere\": {"; ++w.depth;
+                w.nl(); w.out += "\"radius\": " + format_f32(o.radius);
+                --w.depth; w.nl(); w.out += "}";
+            } else if (src.variant == 1) {
+                w.nl(); w.out += "\"MeshFile\": {"; ++w.depth;
+                w.nl(); w.out += "\"path\": "; w.str(src.path); w.out += ",";
+                w.nl(); w.out += "\"scale\": " + format_f32(src.scale);
+                --w.depth; w.nl(); w.out += "}";
+            } else {
+                w.nl(); w.out += "\"Mesh\": {"; ++w.depth;
+                w.nl(); w.out += "\"triangles\": "; w.triangles(sc.triangles.data() + o.tri_begin, o.tri_count); w.out += ",";
+                w.nl(); w.out += "\"bounding_sphere\": {"; ++w.depth;
+                w.nl(); w.out += "\"position\": "; w.vec3(o.bs_position); w.out += ",";
+                w.nl(); w.out += "\"radius\": " + format_f32(o.bs_radius);
+                --w.depth; w.nl(); w.out += "},";
+                w.nl(); w.out += "\"bounding_box\": "; w.triangles(src.bounding_box.data(), src.bounding_box.size());
+                --w.depth; w.nl(); w.out += "}";
+            }
+            --w.depth; w.nl(); w.out += "},";
+            w.nl(); w.out += "\"position\": "; w.vec3(o.position); w.out += ",";
+            w.nl(); w.out += "\"material\": {"; ++w.depth;
+            w.nl(); w.out += "\"color\": "; w.vec3(o.color); w.out += ",";
+            w.nl(); w.out += "\"emmission\": "; w.vec3(o.emission); w.out += ",";
+            w.nl(); w.out += std::string("\"reflect_type\": \"") + kRefl[o.reflect_type] + "\"";
+            --w.depth; w.nl(); w.out += "}";
+            --w.depth; w.nl(); w.out += "}";
+            if (i + 1 < sc.objects.size()) w.out += ",";
+        }
+        --w.depth; w.nl(); w.out += "]";
+    }
+    w.out += ",";
+    w.nl(); w.out += "\"camera\": {"; ++w.depth;
+    w.nl(); w.out += "\"position\": "; w.vec3(sc.camera.position); w.out += ",";
+    w.nl(); w.out += "\"direction\": "; w.vec3(sc.camera.direction); w.out += ",";
+    w.nl(); w.out += "\"focal_length\": " + format_f32(sc.camera.focal_length) + ",";
+    w.nl(); w.out += "\"sensor_width\": " + format_f32(sc.camera.sensor_width) + ",";
+    w.nl(); w.out += "\"aspect_ratio\": " + format_f32(sc.camera.aspect_ratio);
+    --w.depth; w.nl(); w.out += "}";
+    --w.depth; w.nl(); w.out += "}";
+    return w.out;
+}
+
+void save_scene_json(const HostScene &sc, const std::string &json_path) {
+    std::ofstream f(json_path, std::ios::binary);
+    if (!f) throw SceneError(PTB_ERR_IO, "cannot create " + json_path);
+    const std::string text = scene_to_json(sc);
+    f.write(text.data(), static_cast<std::streamsize>(text.size()));
+    if (!f) throw SceneError(PTB_ERR_IO, "write error on " + json_path);
 }
 
 // ------------------------------------------------------------------------------------------------

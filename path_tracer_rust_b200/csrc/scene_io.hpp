@@ -14,9 +14,19 @@ struct SceneError : std::runtime_error {
 };
 
 // SceneData (mod.rs:121-125) in the C ABI's own structs, so it can be handed to ptb_upload_scene directly
+// what SceneObjectDescriptorType (mod.rs:298-302) needs to be written back: the MeshFile descriptor or the inline mesh's
+// serialised bounding box (mod.rs:441-448)
+struct ObjectSource {
+    int variant = 0;  // 0 Sphere, 1 MeshFile, 2 Mesh
+    std::string path;
+    float scale = 1.0f;
+    std::vector<ptb_triangle> bounding_box;
+};
+
 struct HostScene {
     std::string id;
     std::vector<ptb_object> objects;
+    std::vector<ObjectSource> sources;
     std::vector<ptb_triangle> triangles;
     ptb_camera camera{};
     ptb_scene_desc desc{};
@@ -30,6 +40,10 @@ struct HostScene {
 };
 
 HostScene load_scene_json(const std::string &json_path, const std::string &base_dir);
+// SceneData::to_descriptor + SceneDescriptor::save (mod.rs:112-150): serde_json::to_string_pretty layout
+std::string scene_to_json(const HostScene &scene);
+void save_scene_json(const HostScene &scene, const std::string &json_path);
+std::string format_f32(float v);
 void load_off(const std::string &path, float scale, std::vector<ptb_triangle> &out);
 void mesh_bounding_sphere(const ptb_triangle *tris, size_t n, float centre[3], float *radius);
 uint32_t to_int_with_gamma_correction(float x);

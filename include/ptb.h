@@ -89,6 +89,10 @@ typedef struct ptb_stats {
 
 /* ---- host-side scene I/O: SceneDescriptor::load + to_data (mod.rs:92-110, 304-318), load_off.rs:8-85 ---- */
 int ptb_scene_load_json(const char *json_path, const char *base_dir, ptb_scene **out, char *err, size_t errlen);
+/* Opt-in extension, NOT reference behaviour: PTB_LOAD_TRIANGULATE_POLYGONS fan-triangulates OFF faces with more than three
+ * vertices (meshes/hdodec.off has pentagons; load_off.rs:73-76 rejects it and so does ptb_scene_load_json). */
+#define PTB_LOAD_TRIANGULATE_POLYGONS 1u
+int ptb_scene_load_json_ex(const char *json_path, const char *base_dir, uint32_t flags, ptb_scene **out, char *err, size_t errlen);
 const ptb_scene_desc *ptb_scene_get_desc(const ptb_scene *scene);
 /* SceneData::to_descriptor + SceneDescriptor::save (mod.rs:112-150): writes serde_json::to_string_pretty's exact layout
  * (MeshFile objects keep their path + scale, inline meshes their serialised bounding sphere and box). */

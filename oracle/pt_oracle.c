@@ -840,7 +840,7 @@ static int parse_usize_tok(const char *tok, long *out) { /* str::parse::<usize>:
     *out = v;
     return 1;
 }
-static int load_off(const char *path, float scale, tri_t **tris_out, int *ntris_out, char *err, int errlen) {
+static int load_off(const char *path, float scale, int fan_polygons, tri_t **tris_out, int *ntris_out, char *err, int errlen) {
     FILE *f = fopen(path, "r");
     if (!f) { snprintf(err, (size_t)errlen, "cannot open %s", path); return -1; }
     char line[1024];
@@ -868,23 +868,36 @@ static int load_off(const char *path, float scale, tri_t **tris_out, int *ntris_
         if (n != 3 || !ok) { snprintf(err, (size_t)errlen, "Invalid vertex coordinates"); goto done; }
         verts[i] = v_scale(V(c[0], c[1], c[2]), scale); /* load_off.rs:52 */
     }
-    tris = (tri_t *)malloc(sizeof(tri_t) * (size_t)(nf > 0 ? nf : 1));
+    long cap = nf > 0 ? nf : 1, nt = 0;
+    tris = (tri_t *)malloc(sizeof(tri_t) * (size_t)cap);
     for (long i = 0; i < nf; ++i) {
         if (!off_next_line(f, line, sizeof line)) { snprintf(err, (size_t)errlen, "unexpected EOF in faces"); goto done; }
         char copy[1024];
         snprintf(copy, sizeof copy, "%s", line);
-        long idx[4]; int n = 0; ok = 1;
+        long idx[64]; int n = 0; ok = 1;
         for (char *tok = strtok(line, " \t\r\n"); tok; tok = strtok(NULL, " \t\r\n")) {
-            if (n < 4 && !parse_usize_tok(tok, &idx[n])) ok = 0; /* first four tokens are unwrap()ed */
+            if (n < 64 && !parse_usize_tok(tok, &idx[n])) { if (n < 4) ok = 0; else idx[n] = -1; } /* first four tokens are unwrap()ed */
             n++;
+        }
+        if (n >= 4 && ok && idx[0] > 3 && fan_polygons) { /* opt-in, not reference behaviour: fan (v0, v_i, v_i+1) */
+            long cnt = idx[0];
+            int good = cnt < 63 && n >= cnt + 1;
+            for (long k = 1; good && k <= cnt; ++k) good = idx[k] >= 0 && idx[k] < nv;
+            if (!good) { snprintf(err, (size_t)errlen, "Invalid face: %.100s", copy); goto done; }
+            for (long k = 2; k < cnt; ++k) {
+                if (nt == cap) { cap *= 2; tris = (tri_t *)realloc(tris, sizeof(tri_t) * (size_t)cap); }
+                tris[nt].a = verts[idx[1]]; tris[nt].b = verts[idx[k]]; tris[nt].c = verts[idx[k + 1]]; nt++;
+            }
+            continue;
         }
         if (n < 4 || !ok || idx[0] != 3 || idx[1] >= nv || idx[2] >= nv || idx[3] >= nv) {
             snprintf(err, (size_t)errlen, "Invalid face: %.100s", copy);
             goto done;
         }
-        tris[i].a = verts[idx[1]]; tris[i].b = verts[idx[2]]; tris[i].c = verts[idx[3]];
+        if (nt == cap) { cap *= 2; tris = (tri_t *)realloc(tris, sizeof(tri_t) * (size_t)cap); }
+        tris[nt].a = verts[idx[1]]; tris[nt].b = verts[idx[2]]; tris[nt].c = verts[idx[3]]; nt++;
     }
-    *tris_out = tris; *ntris_out = (int)nf; tris = NULL; rc = 0;
+    *tris_out = tris; *ntris_out = (int)nt; tris = NULL; rc = 0;
 done:
     free(verts); free(tris); fclose(f);
     return rc;
@@ -898,6 +911,9 @@ void pto_scene_free(pto_scene *sc) {
 }
 #define FAIL(...) do { snprintf(err, (size_t)errlen, __VA_ARGS__); goto fail; } while (0)
 pto_scene *pto_scene_load(const char *json_path, const char *base_dir, char *err, int errlen) {
+    return pto_scene_load_ex(json_path, base_dir, 0, err, errlen);
+}
+pto_scene *pto_scene_load_ex(const char *json_path, const char *base_dir, int fan_polygons, char *err, int errlen) {
     char dummy[8];
     if (!err) { err = dummy; errlen = sizeof dummy; }
     err[0] = 0;
@@ -952,7 +968,7 @@ pto_scene *pto_scene_load(const char *json_path, const char *base_dir, char *err
             if (jp->str[0] == '/' || !base_dir || !base_dir[0]) snprintf(path, sizeof path, "%s", jp->str);
             else snprintf(path, sizeof path, "%s/%s", base_dir, jp->str);
             char e2[200];
-            if (load_off(path, scale, &o->tris, &o->ntris, e2, sizeof e2)) FAIL("object %d: %s", i, e2);
+            if (load_off(path, scale, fan_polygons, &o->tris, &o->ntris, e2, sizeof e2)) FAIL("object %d: %s", i, e2);
             mesh_bounds(o->tris, o->ntris, &o->bs_pos, &o->bs_radius); /* Mesh::new, load_off.rs:84 */
         } else if (!strcmp(kind, "Mesh")) {
             o->type = OBJ_MESH;

@@ -24,6 +24,8 @@ typedef struct {
 } pto_render_cfg;
 
 pto_scene *pto_scene_load(const char *json_path, const char *base_dir, char *err, int errlen);
+/* fan_polygons != 0: opt-in fan triangulation of n-gon faces (NOT reference behaviour; load_off.rs:73-76 rejects them) */
+pto_scene *pto_scene_load_ex(const char *json_path, const char *base_dir, int fan_polygons, char *err, int errlen);
 void pto_scene_free(pto_scene *sc);
 int pto_scene_counts(const pto_scene *sc, int *nobjs, int *nspheres, int *nmeshes, int *ntris);
 const char *pto_scene_id(const pto_scene *sc);

@@ -66,7 +66,7 @@ _lib = None
 _lib_lock = threading.Lock()
 
 # every symbol include/ptb.h declares
-ABI_SYMBOLS = ["ptb_scene_load_json", "ptb_scene_save_json", "ptb_scene_set_camera", "ptb_scene_get_desc", "ptb_scene_id", "ptb_scene_free", "ptb_abi_version",
+ABI_SYMBOLS = ["ptb_scene_load_json", "ptb_scene_load_json_ex", "ptb_scene_save_json", "ptb_scene_set_camera", "ptb_scene_get_desc", "ptb_scene_id", "ptb_scene_free", "ptb_abi_version",
                "ptb_device_count", "ptb_create", "ptb_destroy", "ptb_last_error", "ptb_upload_scene", "ptb_get_stats", "ptb_set_option", "ptb_selftest",
                "ptb_render", "ptb_render_device", "ptb_resolve_device", "ptb_primary_hits", "ptb_intersect",
                "ptb_to_int_with_gamma_correction", "ptb_write_ppm", "ptb_hash_pixels"]
@@ -85,6 +85,7 @@ def load_library():
         L = C.CDLL(path)
         fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int32)
         L.ptb_scene_load_json.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p), C.c_char_p, C.c_size_t]
+        L.ptb_scene_load_json_ex.argtypes = [C.c_char_p, C.c_char_p, C.c_uint32, C.POINTER(C.c_void_p), C.c_char_p, C.c_size_t]
         L.ptb_scene_save_json.argtypes = [C.c_void_p, C.c_char_p]
         L.ptb_scene_set_camera.argtypes = [C.c_void_p, C.POINTER(_Camera)]
         L.ptb_scene_get_desc.restype = C.POINTER(_SceneDesc)
@@ -144,14 +145,14 @@ class Scene:
         self._id = scene_id
 
     @classmethod
-    def load(cls, scene: str, base_dir: Optional[str] = None) -> "Scene":
+    def load(cls, scene: str, base_dir: Optional[str] = None, triangulate_polygons: bool = False) -> "Scene":
         """SceneDescriptor::load(id) (mod.rs:93-98) + to_data(); `scene` is an id under scenes/ or a .json path."""
         L = load_library()
         base = base_dir or REPO_ROOT
         path = scene if scene.endswith(".json") else os.path.join(base, "scenes", f"{scene}.json")
         h = C.c_void_p()
         err = C.create_string_buffer(512)
-        rc = L.ptb_scene_load_json(path.encode(), base.encode(), C.byref(h), err, 512)
+        rc = L.ptb_scene_load_json_ex(path.encode(), base.encode(), 1 if triangulate_polygons else 0, C.byref(h), err, 512)
         if rc != PTB_OK:
             raise BackendError(rc, err.value.decode())
         return cls(handle=h, desc=L.ptb_scene_get_desc(h), scene_id=L.ptb_scene_id(h).decode())

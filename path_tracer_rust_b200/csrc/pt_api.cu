@@ -112,11 +112,15 @@ double now_ms() {
 // host-side scene I/O
 // ------------------------------------------------------------------------------------------------
 extern "C" int ptb_scene_load_json(const char *json_path, const char *base_dir, ptb_scene **out, char *err, size_t errlen) {
+    return ptb_scene_load_json_ex(json_path, base_dir, 0u, out, err, errlen);
+}
+extern "C" int ptb_scene_load_json_ex(const char *json_path, const char *base_dir, uint32_t flags, ptb_scene **out, char *err,
+                                      size_t errlen) {
     if (err && errlen) err[0] = 0;
     if (!json_path || !out) return fail(nullptr, PTB_ERR_ARG, "ptb_scene_load_json: null argument");
     try {
         auto *s = new ptb_scene;
-        s->host = load_scene_json(json_path, base_dir ? base_dir : "");
+        s->host = load_scene_json(json_path, base_dir ? base_dir : "", flags);
         s->host.refresh_desc();
         *out = s;
         return PTB_OK;

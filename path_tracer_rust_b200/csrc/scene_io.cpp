@@ -221,7 +221,7 @@ bool parse_f32(const std::string &tok, float &out) {  // str::parse::<f32>: corr
 }
 }  // namespace
 
-void load_off(const std::string &path, float scale, std::vector<ptb_triangle> &out) {
+void load_off(const std::string &path, float scale, std::vector<ptb_triangle> &out, unsigned flags) {
     OffLines L;
     L.in.open(path);
     if (!L.in) throw SceneError(PTB_ERR_IO, "cannot open " + path);
@@ -251,15 +251,28 @@ void load_off(const std::string &path, float scale, std::vector<ptb_triangle> &o
         size_t idx[4];
         bool ok = toks.size() >= 4;
         for (int k = 0; ok && k < 4; ++k) ok = parse_usize(toks[static_cast<size_t>(k)], idx[k]);
+        auto emit = [&](size_t ia, size_t ib, size_t ic) {
+            ptb_triangle t;
+            for (int k = 0; k < 3; ++k) {
+                t.a[k] = verts[ia * 3 + static_cast<size_t>(k)];
+                t.b[k] = verts[ib * 3 + static_cast<size_t>(k)];
+                t.c[k] = verts[ic * 3 + static_cast<size_t>(k)];
+            }
+            out.push_back(t);
+        };
+        if (ok && idx[0] > 3 && (flags & PTB_LOAD_TRIANGULATE_POLYGONS)) {
+            // NOT reference behaviour (opt-in): fan-triangulate an n-gon (v0, v_i, v_i+1); the reference rejects it
+            const size_t cnt = idx[0];
+            std::vector<size_t> poly(cnt);
+            bool good = toks.size() >= cnt + 1;
+            for (size_t k = 0; good && k < cnt; ++k) good = parse_usize(toks[k + 1], poly[k]) && poly[k] < nv;
+            if (!good) throw bad("Invalid face: " + line);
+            for (size_t k = 1; k + 1 < cnt; ++k) emit(poly[0], poly[k], poly[k + 1]);
+            continue;
+        }
         // only triangles are supported (load_off.rs:73-76); trailing colour tokens are ignored
         if (!ok || idx[0] != 3 || idx[1] >= nv || idx[2] >= nv || idx[3] >= nv) throw bad("Invalid face: " + line);
-        ptb_triangle t;
-        for (int k = 0; k < 3; ++k) {
-            t.a[k] = verts[idx[1] * 3 + static_cast<size_t>(k)];
-            t.b[k] = verts[idx[2] * 3 + static_cast<size_t>(k)];
-            t.c[k] = verts[idx[3] * 3 + static_cast<size_t>(k)];
-        }
-        out.push_back(t);
+        emit(idx[1], idx[2], idx[3]);
     }
 }
 
@@ -275,7 +288,7 @@ static int parse_reflect_type(const Json *j) {
     throw SceneError(PTB_ERR_PARSE, "unknown variant `" + j->text + "`, expected one of `Diffuse`, `Specular`, `Refract`");
 }
 
-HostScene load_scene_json(const std::string &json_path, const std::string &base_dir) {
+HostScene load_scene_json(const std::string &json_path, const std::string &base_dir, unsigned flags) {
     std::ifstream in(json_path, std::ios::binary);
     if (!in) throw SceneError(PTB_ERR_IO, "cannot open " + json_path);
     std::stringstream buf;
@@ -328,7 +341,7 @@ HostScene load_scene_json(const std::string &json_path, const std::string &base_
                 std::string full = p->text;
                 if (!full.empty() && full[0] != '/' && !base_dir.empty()) full = base_dir + "/" + full;
                 src.variant = 1; src.path = p->text; src.scale = scale;
-                load_off(full, scale, sc.triangles);
+                load_off(full, scale, sc.triangles, flags);
                 o.tri_count = sc.triangles.size() - o.tri_begin;
                 mesh_bounding_sphere(sc.triangles.data() + o.tri_begin, o.tri_count, o.bs_position, &o.bs_radius);
             } else if (variant == "Mesh") {

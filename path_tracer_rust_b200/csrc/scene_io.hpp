@@ -39,12 +39,12 @@ struct HostScene {
     }
 };
 
-HostScene load_scene_json(const std::string &json_path, const std::string &base_dir);
+HostScene load_scene_json(const std::string &json_path, const std::string &base_dir, unsigned flags = 0);
 // SceneData::to_descriptor + SceneDescriptor::save (mod.rs:112-150): serde_json::to_string_pretty layout
 std::string scene_to_json(const HostScene &scene);
 void save_scene_json(const HostScene &scene, const std::string &json_path);
 std::string format_f32(float v);
-void load_off(const std::string &path, float scale, std::vector<ptb_triangle> &out);
+void load_off(const std::string &path, float scale, std::vector<ptb_triangle> &out, unsigned flags = 0);
 void mesh_bounding_sphere(const ptb_triangle *tris, size_t n, float centre[3], float *radius);
 uint32_t to_int_with_gamma_correction(float x);
 void write_ppm(const std::string &path, const float *mean_rgb, int W, int H, uint64_t spp, const std::string &scene_id,

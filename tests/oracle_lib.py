@@ -46,6 +46,8 @@ def lib():
     u64p = C.POINTER(C.c_uint64)
     L.pto_scene_load.restype = C.c_void_p
     L.pto_scene_load.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
+    L.pto_scene_load_ex.restype = C.c_void_p
+    L.pto_scene_load_ex.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int]
     L.pto_scene_free.argtypes = [C.c_void_p]
     L.pto_scene_counts.argtypes = [C.c_void_p, ip, ip, ip, ip]
     L.pto_scene_id.restype = C.c_char_p
@@ -91,11 +93,11 @@ def f32(*v):
 class OracleScene:
     """A scene loaded by the oracle's own JSON/OFF reader (mod.rs:92-110, load_off.rs)."""
 
-    def __init__(self, json_path: str, base_dir: str | None = None):
+    def __init__(self, json_path: str, base_dir: str | None = None, fan_polygons: bool = False):
         L = lib()
         err = C.create_string_buffer(512)
         base = base_dir if base_dir is not None else ROOT
-        self.h = L.pto_scene_load(json_path.encode(), base.encode(), err, 512)
+        self.h = L.pto_scene_load_ex(json_path.encode(), base.encode(), 1 if fan_polygons else 0, err, 512)
         if not self.h:
             raise ValueError(err.value.decode())
         self.path = json_path

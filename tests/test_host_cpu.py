@@ -212,3 +212,18 @@ def test_scene_save_float_formatting_and_camera_edit(P, tmp_path):
     assert back["camera"]["position"] == [1.5, 2.0, -3.25] and back["camera"]["focal_length"] == 0.05
     text = out.read_text()
     assert '"radius": 1.0\n' in text and '"radius": 1e-7\n' in text and '"radius": 16777216.0\n' in text and '"radius": 0.00001\n' in text
+
+
+def test_polygon_fan_is_opt_in_and_loaders_agree(P):
+    """meshes/hdodec.off (pentagons): rejected by default like load_off.rs:73-76; with the opt-in flag both independent loaders
+    fan-triangulate it identically (12 pentagons -> 36 triangles).  No reference oracle exists for this mesh."""
+    with pytest.raises(P.BackendError, match="Invalid face"):
+        P.Scene.load("mesh-hdodec")
+    with pytest.raises(ValueError, match="Invalid face"):
+        O.OracleScene(scene_path("mesh-hdodec"))
+    sc = P.Scene.load("mesh-hdodec", triangulate_polygons=True)
+    osc = O.OracleScene(scene_path("mesh-hdodec"), fan_polygons=True)
+    assert sc.n_triangles == 810 + 14 + 36 == osc.counts()["triangles"]
+    hd = sc.objects()[1]
+    p, r = osc.mesh_bounds(1)
+    assert hd.tri_count == 36 and list(hd.bs_position) == p.tolist() and f32(hd.bs_radius) == r

@@ -98,17 +98,22 @@ def test_intersect_arbitrary_rays_bit_exact(be, sid):
 @pytest.mark.parametrize("sid,W,H,spp", [("cornell", 96, 64, 16), ("mesh", 60, 40, 4), ("single-sphere", 96, 64, 8),
                                          ("two-spheres", 96, 64, 8), ("three-spheres", 96, 64, 8), ("cartesian", 48, 32, 4),
                                          ("cornell", 37, 23, 5)])
-def test_lockstep_framebuffer_bit_exact(be, sid, W, H, spp):
+@pytest.mark.parametrize("integrator", [1, 2])          # 1 = megakernel, 2 = wavefront (auto would pick by image size)
+def test_lockstep_framebuffer_bit_exact(be, sid, W, H, spp, integrator):
     import path_tracer_rust_b200.api as A
-    _, osc = load_both(be, sid)
-    g = be.render(W, H, spp, seed=42, out_kind=A.PTB_OUT_SUM)
-    o, ost = osc.render_sum(W, H, spp, seed=42, rng=O.RNG_PHILOX, sincos=O.SINCOS_DET, accum=O.ACCUM_FORWARD)
-    st = be.stats()
-    assert st["segments"] == int(ost[0])                 # identical path geometry
-    assert st["samples"] == W * H * spp
-    assert np.array_equal(bits(g), bits(o))
-    gm = be.render(W, H, spp, seed=42, out_kind=A.PTB_OUT_MEAN)
-    assert np.array_equal(bits(gm), bits(O.resolve(o, spp)))
+    be.set_option("integrator", integrator)
+    try:
+        _, osc = load_both(be, sid)
+        g = be.render(W, H, spp, seed=42, out_kind=A.PTB_OUT_SUM)
+        o, ost = osc.render_sum(W, H, spp, seed=42, rng=O.RNG_PHILOX, sincos=O.SINCOS_DET, accum=O.ACCUM_FORWARD)
+        st = be.stats()
+        assert st["segments"] == int(ost[0])                 # identical path geometry
+        assert st["samples"] == W * H * spp
+        assert np.array_equal(bits(g), bits(o))
+        gm = be.render(W, H, spp, seed=42, out_kind=A.PTB_OUT_MEAN)
+        assert np.array_equal(bits(gm), bits(O.resolve(o, spp)))
+    finally:
+        be.set_option("integrator", 0)
 
 
 def test_batch_and_offset_invariance(be):

@@ -214,8 +214,14 @@ def main():
     def step_resident():
         return render_sharded(shard, spp, rank, world)
 
+    host_np = host_img.numpy().reshape(-1, 3) if rank == 0 else None
+
     def step_e2e():
         be.upload_scene(scene)                       # H2D of the scene (flatten + upload + device BVH build)
+        if world == 1:
+            # the reference-facing call itself: ptb_render() with a HOST output buffer (here pinned), blocking like render()
+            be.render(W, H, spp, seed=2026, out=host_np)
+            return float(host_np[0, 0])
         img = render_sharded(shard, spp, rank, world)
         if rank == 0:
             host_img.copy_(img, non_blocking=True)   # D2H of the resolved image

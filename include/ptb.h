@@ -143,6 +143,23 @@ int ptb_render_device(ptb_ctx *ctx, int width, int height, uint64_t spp_begin, u
 int ptb_resolve_device(ptb_ctx *ctx, const float *d_sum_rgb, uint64_t n_floats, uint64_t spp_total, float *d_mean_rgb,
                        void *cuda_stream);
 
+/* ---- multi-GPU reduce without a library collective on the data path --------------------------------------------
+ * One process per GPU.  Every rank renders its share of the samples into a sum framebuffer obtained from ptb_device_alloc,
+ * exports it (CUDA IPC), opens the other ranks' buffers, and after a barrier reduces + resolves ITS slice of the image straight
+ * out of peer memory over NVLink into rank 0's output buffer: one kernel does the sum over ranks (fixed rank order, so the image
+ * is deterministic), the division by spp, the clamp (mod.rs:849-856) and the P2P store.  See path_tracer_rust_b200/distributed.py. */
+int ptb_device_alloc(ptb_ctx *ctx, uint64_t n_bytes, void **d_ptr);
+int ptb_device_free(ptb_ctx *ctx, void *d_ptr);
+int ptb_device_memset(ptb_ctx *ctx, void *d_ptr, int value, uint64_t n_bytes, void *cuda_stream);
+int ptb_device_to_host(ptb_ctx *ctx, void *host_dst, const void *d_src, uint64_t n_bytes, void *cuda_stream); /* blocking */
+int ptb_device_sync(ptb_ctx *ctx, void *cuda_stream);
+int ptb_ipc_export(ptb_ctx *ctx, const void *d_ptr, unsigned char handle64[64]);
+int ptb_ipc_open(ptb_ctx *ctx, const unsigned char handle64[64], void **d_ptr);
+int ptb_ipc_close(ptb_ctx *ctx, void *d_ptr);
+/* d_dst[i] = clamp((sum_g d_peer_sums[g][i]) / spp_total, 0, 1) for i in [first_float, first_float + n_floats) */
+int ptb_peer_reduce_resolve(ptb_ctx *ctx, const float *const *d_peer_sums, int n_peers, uint64_t first_float, uint64_t n_floats,
+                            uint64_t spp_total, float *d_dst, void *cuda_stream);
+
 /* ---- parity hooks ----------------------------------------------------------------------------- */
 /* intersect_scene (mod.rs:631-659) for the deterministic centre ray of every pixel (xsub=ysub=xfilter=yfilter=0
  * in mod.rs:833-838).  obj = object index or -1, tri = triangle index inside the mesh or -1, t = distance. */

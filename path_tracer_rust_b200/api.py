@@ -69,7 +69,9 @@ _lib_lock = threading.Lock()
 ABI_SYMBOLS = ["ptb_scene_load_json", "ptb_scene_load_json_ex", "ptb_scene_save_json", "ptb_scene_set_camera", "ptb_scene_get_desc", "ptb_scene_id", "ptb_scene_free", "ptb_abi_version",
                "ptb_device_count", "ptb_create", "ptb_destroy", "ptb_last_error", "ptb_upload_scene", "ptb_get_stats", "ptb_set_option", "ptb_selftest",
                "ptb_render", "ptb_render_device", "ptb_resolve_device", "ptb_primary_hits", "ptb_intersect",
-               "ptb_to_int_with_gamma_correction", "ptb_write_ppm", "ptb_hash_pixels"]
+               "ptb_to_int_with_gamma_correction", "ptb_write_ppm", "ptb_hash_pixels", "ptb_device_alloc", "ptb_device_free",
+               "ptb_device_memset", "ptb_device_to_host", "ptb_device_sync", "ptb_ipc_export", "ptb_ipc_open", "ptb_ipc_close",
+               "ptb_peer_reduce_resolve"]
 
 
 def load_library():
@@ -107,6 +109,15 @@ def load_library():
                                         C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]
         L.ptb_resolve_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
         L.ptb_primary_hits.argtypes = [C.c_void_p, C.c_int, C.c_int, ip, ip, fp]
+        L.ptb_device_alloc.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
+        L.ptb_device_free.argtypes = [C.c_void_p, C.c_void_p]
+        L.ptb_device_memset.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_void_p]
+        L.ptb_device_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+        L.ptb_device_sync.argtypes = [C.c_void_p, C.c_void_p]
+        L.ptb_ipc_export.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p]
+        L.ptb_ipc_open.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]
+        L.ptb_ipc_close.argtypes = [C.c_void_p, C.c_void_p]
+        L.ptb_peer_reduce_resolve.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
         L.ptb_intersect.argtypes = [C.c_void_p, fp, C.c_uint64, ip, ip, fp, fp, fp]
         L.ptb_to_int_with_gamma_correction.restype = C.c_uint32
         L.ptb_to_int_with_gamma_correction.argtypes = [C.c_float]
@@ -332,6 +343,42 @@ class Backend:
     def resolve_device(self, d_sum_ptr: int, n_floats: int, spp_total: int, d_mean_ptr: int, stream: int = 0):
         self._check(self.L.ptb_resolve_device(self._h, C.c_void_p(d_sum_ptr), n_floats, spp_total, C.c_void_p(d_mean_ptr),
                                               C.c_void_p(stream)))
+
+    # ---- device buffers / CUDA IPC / peer reduce (multi-GPU driver) ----
+    def device_alloc(self, n_bytes: int) -> int:
+        p = C.c_void_p()
+        self._check(self.L.ptb_device_alloc(self._h, n_bytes, C.byref(p)))
+        return int(p.value)
+
+    def device_free(self, ptr: int):
+        self._check(self.L.ptb_device_free(self._h, C.c_void_p(ptr)))
+
+    def device_memset(self, ptr: int, value: int, n_bytes: int, stream: int = 0):
+        self._check(self.L.ptb_device_memset(self._h, C.c_void_p(ptr), value, n_bytes, C.c_void_p(stream)))
+
+    def device_to_host(self, host: np.ndarray, ptr: int, stream: int = 0):
+        self._check(self.L.ptb_device_to_host(self._h, host.ctypes.data_as(C.c_void_p), C.c_void_p(ptr), host.nbytes, C.c_void_p(stream)))
+
+    def device_sync(self, stream: int = 0):
+        self._check(self.L.ptb_device_sync(self._h, C.c_void_p(stream)))
+
+    def ipc_export(self, ptr: int) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._check(self.L.ptb_ipc_export(self._h, C.c_void_p(ptr), buf))
+        return buf.raw
+
+    def ipc_open(self, handle: bytes) -> int:
+        p = C.c_void_p()
+        self._check(self.L.ptb_ipc_open(self._h, handle, C.byref(p)))
+        return int(p.value)
+
+    def ipc_close(self, ptr: int):
+        self._check(self.L.ptb_ipc_close(self._h, C.c_void_p(ptr)))
+
+    def peer_reduce_resolve(self, peer_ptrs, first_float: int, n_floats: int, spp_total: int, dst_ptr: int, stream: int = 0):
+        arr = (C.c_void_p * len(peer_ptrs))(*peer_ptrs)
+        self._check(self.L.ptb_peer_reduce_resolve(self._h, arr, len(peer_ptrs), first_float, n_floats, spp_total, C.c_void_p(dst_ptr),
+                                                   C.c_void_p(stream)))
 
     def primary_hits(self, width: int, height: int):
         n = width * height

@@ -511,6 +511,77 @@ extern "C" int ptb_render(ptb_ctx *ctx, int width, int height, uint64_t spp_begi
 }
 
 // ------------------------------------------------------------------------------------------------
+// multi-GPU: device buffers, CUDA IPC, peer reduce + resolve
+// ------------------------------------------------------------------------------------------------
+extern "C" int ptb_device_alloc(ptb_ctx *ctx, uint64_t n_bytes, void **d_ptr) {
+    if (!ctx || !d_ptr || n_bytes == 0) return fail(ctx, PTB_ERR_ARG, "ptb_device_alloc: bad argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMalloc(d_ptr, n_bytes));
+    return PTB_OK;
+}
+extern "C" int ptb_device_free(ptb_ctx *ctx, void *d_ptr) {
+    if (!ctx) return fail(ctx, PTB_ERR_ARG, "ptb_device_free: ctx is null");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaFree(d_ptr));
+    return PTB_OK;
+}
+extern "C" int ptb_device_memset(ptb_ctx *ctx, void *d_ptr, int value, uint64_t n_bytes, void *cuda_stream) {
+    if (!ctx || !d_ptr) return fail(ctx, PTB_ERR_ARG, "ptb_device_memset: bad argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemsetAsync(d_ptr, value, n_bytes, static_cast<cudaStream_t>(cuda_stream)));
+    return PTB_OK;
+}
+extern "C" int ptb_device_to_host(ptb_ctx *ctx, void *host_dst, const void *d_src, uint64_t n_bytes, void *cuda_stream) {
+    if (!ctx || !host_dst || !d_src) return fail(ctx, PTB_ERR_ARG, "ptb_device_to_host: bad argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemcpyAsync(host_dst, d_src, n_bytes, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(cuda_stream)));
+    CU(ctx, cudaStreamSynchronize(static_cast<cudaStream_t>(cuda_stream)));
+    return PTB_OK;
+}
+extern "C" int ptb_device_sync(ptb_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return fail(ctx, PTB_ERR_ARG, "ptb_device_sync: ctx is null");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(static_cast<cudaStream_t>(cuda_stream)));
+    return PTB_OK;
+}
+extern "C" int ptb_ipc_export(ptb_ctx *ctx, const void *d_ptr, unsigned char handle64[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    if (!ctx || !d_ptr || !handle64) return fail(ctx, PTB_ERR_ARG, "ptb_ipc_export: bad argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    CU(ctx, cudaIpcGetMemHandle(&h, const_cast<void *>(d_ptr)));
+    std::memcpy(handle64, &h, 64);
+    return PTB_OK;
+}
+extern "C" int ptb_ipc_open(ptb_ctx *ctx, const unsigned char handle64[64], void **d_ptr) {
+    if (!ctx || !d_ptr || !handle64) return fail(ctx, PTB_ERR_ARG, "ptb_ipc_open: bad argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle64, 64);
+    CU(ctx, cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return PTB_OK;
+}
+extern "C" int ptb_ipc_close(ptb_ctx *ctx, void *d_ptr) {
+    if (!ctx || !d_ptr) return fail(ctx, PTB_ERR_ARG, "ptb_ipc_close: bad argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaIpcCloseMemHandle(d_ptr));
+    return PTB_OK;
+}
+extern "C" int ptb_peer_reduce_resolve(ptb_ctx *ctx, const float *const *d_peer_sums, int n_peers, uint64_t first_float,
+                                       uint64_t n_floats, uint64_t spp_total, float *d_dst, void *cuda_stream) {
+    if (!ctx || !d_peer_sums || !d_dst || spp_total == 0) return fail(ctx, PTB_ERR_ARG, "ptb_peer_reduce_resolve: bad argument");
+    if (n_peers < 1 || n_peers > MAX_PEERS) return fail(ctx, PTB_ERR_LIMIT, "ptb_peer_reduce_resolve: 1..16 peers");
+    CU(ctx, cudaSetDevice(ctx->device));
+    PeerPtrs pp{};
+    for (int g = 0; g < n_peers; ++g) {
+        if (!d_peer_sums[g]) return fail(ctx, PTB_ERR_ARG, "ptb_peer_reduce_resolve: null peer pointer");
+        pp.p[g] = d_peer_sums[g];
+    }
+    CU(ctx, launch_peer_reduce_resolve(pp, n_peers, first_float, n_floats, spp_total, d_dst, ctx->sm_count, static_cast<cudaStream_t>(cuda_stream)));
+    return PTB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // parity hooks
 // ------------------------------------------------------------------------------------------------
 static int run_intersect(ptb_ctx *ctx, const float *rays6, uint64_t n, int pw, int ph, int32_t *obj, int32_t *tri, float *t,

@@ -189,6 +189,40 @@ __global__ void k_resolve(const float *__restrict__ sum, unsigned long long n, f
     }
 }
 
+// Multi-GPU: sum the ranks' partial framebuffers (peer memory, NVLink loads), resolve, store (possibly into a peer's buffer).
+// The order of the adds is the rank order, whatever the interconnect does: ((fb0 + fb1) + fb2) + ...
+__global__ void __launch_bounds__(256) k_peer_reduce_resolve(const PeerPtrs peers, int n_peers, unsigned long long first,
+                                                             unsigned long long n, float spp, float *__restrict__ dst) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((first & 3ull) == 0) {  // 16-byte path
+        const unsigned long long n4 = n / 4;
+        for (unsigned long long i = tid; i < n4; i += stride) {
+            const unsigned long long at = first / 4 + i;
+            float4 s = reinterpret_cast<const float4 *>(peers.p[0])[at];
+            for (int g = 1; g < n_peers; ++g) {
+                const float4 v = reinterpret_cast<const float4 *>(peers.p[g])[at];
+                s.x = s.x + v.x; s.y = s.y + v.y; s.z = s.z + v.z; s.w = s.w + v.w;
+            }
+            float4 r;
+            r.x = fminf(fmaxf(PTB_DIV(s.x, spp), 0.0f), 1.0f); r.y = fminf(fmaxf(PTB_DIV(s.y, spp), 0.0f), 1.0f);
+            r.z = fminf(fmaxf(PTB_DIV(s.z, spp), 0.0f), 1.0f); r.w = fminf(fmaxf(PTB_DIV(s.w, spp), 0.0f), 1.0f);
+            reinterpret_cast<float4 *>(dst)[at] = r;
+        }
+        for (unsigned long long i = n4 * 4 + tid; i < n; i += stride) {
+            float s = peers.p[0][first + i];
+            for (int g = 1; g < n_peers; ++g) s = s + peers.p[g][first + i];
+            dst[first + i] = fminf(fmaxf(PTB_DIV(s, spp), 0.0f), 1.0f);
+        }
+    } else {
+        for (unsigned long long i = tid; i < n; i += stride) {
+            float s = peers.p[0][first + i];
+            for (int g = 1; g < n_peers; ++g) s = s + peers.p[g][first + i];
+            dst[first + i] = fminf(fmaxf(PTB_DIV(s, spp), 0.0f), 1.0f);
+        }
+    }
+}
+
 // exhaustive check of rcp_rn_normal against __frcp_rn over every float whose exponent field is in [1, 252]
 __global__ void k_rcp_selftest(unsigned long long *mismatches) {
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
@@ -251,6 +285,16 @@ cudaError_t launch_render(const DScene &sc, const RenderArgs &a, int sm_count, c
     if (blocks > need) blocks = need;
     if (blocks < 1) blocks = 1;
     kern<<<(unsigned)blocks, RENDER_THREADS, smem, st>>>(sc, a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_peer_reduce_resolve(const PeerPtrs &peers, int n_peers, unsigned long long first, unsigned long long n,
+                                       unsigned long long spp, float *d_dst, int sm_count, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    unsigned long long blocks = (n / 4 + 255) / 256 + 1;
+    const unsigned long long cap = (unsigned long long)sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    k_peer_reduce_resolve<<<(unsigned)blocks, 256, 0, st>>>(peers, n_peers, first, n, (float)spp, d_dst);
     return cudaGetLastError();
 }
 

@@ -27,6 +27,10 @@ cudaError_t launch_contraction_probe(float a, float b, float c, float *d_out, cu
 cudaError_t launch_intersect(const DScene &sc, const float *d_rays, unsigned long long n, int pw, int ph, int *d_obj, int *d_tri,
                              float *d_t, float *d_point, float *d_normal, int sm_count, cudaStream_t st);
 cudaError_t launch_render(const DScene &sc, const RenderArgs &a, int sm_count, cudaStream_t st);
+constexpr int MAX_PEERS = 16;
+struct PeerPtrs { const float *p[MAX_PEERS]; };
+cudaError_t launch_peer_reduce_resolve(const PeerPtrs &peers, int n_peers, unsigned long long first, unsigned long long n,
+                                       unsigned long long spp, float *d_dst, int sm_count, cudaStream_t st);
 cudaError_t launch_resolve(const float *d_sum, unsigned long long n, unsigned long long spp, float *d_mean, int sm_count,
                            cudaStream_t st);
 

@@ -60,3 +60,83 @@ def render_sharded(renderer: ShardRenderer, spp_total: int, rank: int = 0, world
     if rank != dst:
         return None
     return renderer.resolve(fb, spp_total)
+
+
+def slice_floats(n_floats: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """16-byte aligned [first, first+count) slice of the framebuffer that `rank` reduces and resolves."""
+    quads = (n_floats + 3) // 4
+    q0, q1 = rank * quads // world_size, (rank + 1) * quads // world_size
+    first, end = min(q0 * 4, n_floats), min(q1 * 4, n_floats)
+    return first, end - first
+
+
+class PeerMemoryFrame:
+    """Multi-GPU frame driver that keeps the reduction on NVLink peer memory instead of a library collective.
+
+    Every rank owns a sum framebuffer allocated by its ptb_ctx and exported with CUDA IPC; rank `dst` additionally owns the
+    output image.  A frame is: render own sample shard -> barrier -> ONE kernel per rank that loads its slice of every rank's
+    framebuffer over NVLink, adds them in rank order (deterministic), divides by spp, clamps (mod.rs:849-856) and stores the
+    result straight into rank dst's output buffer -> barrier -> rank dst copies the image to the host.
+    torch.distributed is used for the handle exchange and the barriers only.
+    """
+
+    def __init__(self, backend, width: int, height: int, seed: int, rank: int, world_size: int, group=None, dst: int = 0):
+        import torch.distributed as dist
+        self.be, self.W, self.H, self.seed = backend, width, height, seed
+        self.rank, self.world, self.group, self.dst, self.dist = rank, world_size, group, dst, dist
+        self.n_floats = width * height * 3
+        self.fb = backend.device_alloc(self.n_floats * 4)
+        self.out = backend.device_alloc(self.n_floats * 4) if rank == dst else 0
+        mine = {"fb": backend.ipc_export(self.fb), "out": backend.ipc_export(self.out) if rank == dst else None}
+        handles = [None] * world_size
+        if world_size > 1:
+            dist.all_gather_object(handles, mine, group=group)
+        else:
+            handles = [mine]
+        self._opened = []
+        self.peer_fb = []
+        for g, h in enumerate(handles):
+            if g == rank:
+                self.peer_fb.append(self.fb)
+            else:
+                p = backend.ipc_open(h["fb"])
+                self._opened.append(p)
+                self.peer_fb.append(p)
+        if rank == dst:
+            self.dst_out = self.out
+        else:
+            self.dst_out = backend.ipc_open(handles[dst]["out"])
+            self._opened.append(self.dst_out)
+
+    def _barrier(self):
+        if self.world > 1:
+            self.dist.barrier(group=self.group)
+
+    def render(self, spp_total: int, host_out=None):
+        """One frame.  Returns the host image (numpy [W*H,3]) on rank dst, None elsewhere."""
+        import numpy as np
+        begin, count = shard_samples(spp_total, self.world, self.rank)
+        self.be.device_memset(self.fb, 0, self.n_floats * 4)
+        if count > 0:
+            self.be.render_device(self.W, self.H, count, self.fb, spp_begin=begin, seed=self.seed, stream=0)
+        self.be.device_sync()
+        self._barrier()                                    # every partial sum is complete and visible
+        first, n = slice_floats(self.n_floats, self.world, self.rank)
+        self.be.peer_reduce_resolve(self.peer_fb, first, n, spp_total, self.dst_out)
+        self.be.device_sync()
+        self._barrier()                                    # every slice has landed in rank dst's buffer
+        if self.rank != self.dst:
+            return None
+        img = host_out if host_out is not None else np.empty((self.W * self.H, 3), np.float32)
+        self.be.device_to_host(img, self.out)
+        return img
+
+    def close(self):
+        self._barrier()
+        for p in self._opened:
+            self.be.ipc_close(p)
+        self._opened = []
+        self._barrier()
+        self.be.device_free(self.fb)
+        if self.out:
+            self.be.device_free(self.out)

@@ -168,6 +168,8 @@ def main():
     ap.add_argument("--workload", default="cornell4k", choices=sorted(WORKLOADS))
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (development only; recorded in config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--reduce", default="peer", choices=["peer", "nccl"],
+                    help="N>1: sum the ranks' framebuffers with the fused peer-memory kernel (default) or with an NCCL reduce")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -180,7 +182,7 @@ def main():
     import numpy as np
     import torch
     import path_tracer_rust_b200 as P
-    from path_tracer_rust_b200.distributed import CudaShardRenderer, render_sharded, shard_samples
+    from path_tracer_rust_b200.distributed import CudaShardRenderer, PeerMemoryFrame, render_sharded, shard_samples
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the backend has no CPU fallback (use --impl reference for the CPU path)")
@@ -201,7 +203,9 @@ def main():
     scene = P.Scene.load(scene_path, base_dir=scene_base)
     be = P.Backend(local_rank)
     be.upload_scene(scene)
-    shard = CudaShardRenderer(be, W, H, seed=2026, device=dev)
+    use_peer = world > 1 and args.reduce == "peer"
+    shard = CudaShardRenderer(be, W, H, seed=2026, device=dev) if not use_peer else None
+    frame = PeerMemoryFrame(be, W, H, seed=2026, rank=rank, world_size=world) if use_peer else None
     nfl = W * H * 3
     host_img = torch.empty(nfl, dtype=torch.float32).pin_memory() if rank == 0 else None
     l2_flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
@@ -212,6 +216,8 @@ def main():
         torch.cuda.synchronize()
 
     def step_resident():
+        if use_peer:
+            return frame.render(spp, to_host=False)
         return render_sharded(shard, spp, rank, world)
 
     host_np = host_img.numpy().reshape(-1, 3) if rank == 0 else None
@@ -222,6 +228,9 @@ def main():
             # the reference-facing call itself: ptb_render() with a HOST output buffer (here pinned), blocking like render()
             be.render(W, H, spp, seed=2026, out=host_np)
             return float(host_np[0, 0])
+        if use_peer:
+            frame.render(spp, host_out=host_np)      # reduce + resolve over peer memory, then D2H on rank 0
+            return float(host_np[0, 0]) if rank == 0 else None
         img = render_sharded(shard, spp, rank, world)
         if rank == 0:
             host_img.copy_(img, non_blocking=True)   # D2H of the resolved image
@@ -250,7 +259,7 @@ def main():
         times.append(e0.elapsed_time(e1))
         st = be.stats()
         seg_total += st["segments"]
-        launches += st["kernel_launches"] + (1 if rank == 0 else 0)
+        launches += st["kernel_launches"] + (1 if (rank == 0 or use_peer) else 0)
     barrier()
     clocks = sampler.stop()
     kernel_ms_last = be.stats()["render_ms"]
@@ -321,7 +330,7 @@ def main():
             "ms_per_step": total_ms / max(args.steps, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: scenes/{scene_id}.json {W}x{H} x {spp} spp, spp sharded over {world} GPU(s), "
-                                   "NCCL fp32 sum-reduce", "scene": scene_id, "width": W, "height": H, "spp": spp,
+                                   + ("fused peer-memory reduce+resolve kernel over NVLink (CUDA IPC)" if use_peer else "NCCL fp32 sum-reduce"), "scene": scene_id, "width": W, "height": H, "spp": spp,
                        "spp_reduced_for_development": reduced, "l2": "flushed between steps (256 MiB device write)",
                        "parallelism": f"spp-shard x{world}"},
             "mray_segments_per_s": seg_rate, "segments_per_sample": seg_total / (samples_per_step * args.steps),
@@ -338,6 +347,8 @@ def main():
                               "sample": cpu["sample"], "mray_segments_per_s": cpu["mseg_s"]} if cpu else None),
         }
         print(json.dumps(line), flush=True)
+    if frame is not None:
+        frame.close()
     if dist is not None:
         dist.destroy_process_group()
     be.close()

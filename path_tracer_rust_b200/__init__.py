@@ -7,7 +7,7 @@ library and a B200.
 """
 from .api import (Backend, BackendError, Image, RenderConfig, RenderDone, RenderUpdate, Resolution, Scene,
                   gamma_correction, library_path, load_library, render, to_int_with_gamma_correction)
-from .distributed import render_sharded
+from .distributed import PeerMemoryFrame, render_sharded
 
 __all__ = ["Backend", "BackendError", "Image", "RenderConfig", "RenderDone", "RenderUpdate", "Resolution", "Scene",
-           "gamma_correction", "library_path", "load_library", "render", "render_sharded", "to_int_with_gamma_correction"]
+           "gamma_correction", "library_path", "load_library", "render", "render_sharded", "PeerMemoryFrame", "to_int_with_gamma_correction"]

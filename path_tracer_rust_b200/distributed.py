@@ -112,8 +112,9 @@ class PeerMemoryFrame:
         if self.world > 1:
             self.dist.barrier(group=self.group)
 
-    def render(self, spp_total: int, host_out=None):
-        """One frame.  Returns the host image (numpy [W*H,3]) on rank dst, None elsewhere."""
+    def render(self, spp_total: int, host_out=None, to_host: bool = True):
+        """One frame.  Returns the host image (numpy [W*H,3]) on rank dst (None elsewhere, or when to_host is False and the
+        resolved image is left in rank dst's device buffer `self.out`)."""
         import numpy as np
         begin, count = shard_samples(spp_total, self.world, self.rank)
         self.be.device_memset(self.fb, 0, self.n_floats * 4)
@@ -125,7 +126,7 @@ class PeerMemoryFrame:
         self.be.peer_reduce_resolve(self.peer_fb, first, n, spp_total, self.dst_out)
         self.be.device_sync()
         self._barrier()                                    # every slice has landed in rank dst's buffer
-        if self.rank != self.dst:
+        if self.rank != self.dst or not to_host:
             return None
         img = host_out if host_out is not None else np.empty((self.W * self.H, 3), np.float32)
         self.be.device_to_host(img, self.out)

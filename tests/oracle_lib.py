@@ -103,8 +103,11 @@ class OracleScene:
         self.path = json_path
 
     def __del__(self):
-        if getattr(self, "h", None):
-            lib().pto_scene_free(self.h)
+        if getattr(self, "h", None) and lib is not None:   # `lib` may already be torn down at interpreter exit
+            try:
+                lib().pto_scene_free(self.h)
+            except Exception:
+                pass
             self.h = None
 
     @property

@@ -344,3 +344,22 @@ def test_hdodec_fan_triangulated_scene(be):
     fb = be.render(W, H, spp, seed=4, out_kind=A.PTB_OUT_SUM)
     ofb, ost = osc.render_sum(W, H, spp, seed=4)
     assert be.stats()["segments"] == int(ost[0]) and np.array_equal(bits(fb), bits(ofb))
+
+
+def test_peer_memory_frame_single_rank(be):
+    """The fused reduce + resolve kernel and the IPC export path with one rank (the N-rank case runs in tools/check_peer_reduce.py
+    under torchrun: bit-exact against rank-ordered oracle partial sums at 2 and 8 GPUs)."""
+    import path_tracer_rust_b200 as P
+    import path_tracer_rust_b200.api as A
+    be.upload_scene(P.Scene.load("cornell"))
+    W, H, spp = 70, 50, 9
+    frame = P.PeerMemoryFrame(be, W, H, seed=8, rank=0, world_size=1)
+    try:
+        assert len(be.ipc_export(frame.fb)) == 64
+        img = frame.render(spp)
+        want = be.render(W, H, spp, seed=8, out_kind=A.PTB_OUT_MEAN)
+        assert np.array_equal(bits(img), bits(want))
+        osc = O.OracleScene(scene_path("cornell"))
+        assert np.array_equal(bits(img), bits(O.resolve(osc.render_sum(W, H, spp, seed=8)[0], spp)))
+    finally:
+        frame.close()

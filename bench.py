@@ -314,6 +314,15 @@ def main():
             tps = dict(tps, bvh_nodes=0.0)
             dominant = "k_render"
         flops_per_seg = 17.0 * (tps["sphere"] + tps["gate"]) + 45.0 * tps["triangle"] + 30.0 * tps["bvh_nodes"] + 120.0
+        # secondary (HBM) view for BVH scenes, SURVEY.md 8d: 32 B per box tested (4 per node visit), 48 B per primitive, ray state in
+        # and out of the HBM queues (4 x float4 + 12 B hit, read by trace + shade, written by shade)
+        hbm = None
+        if tps["bvh_nodes"] > 0:
+            bytes_per_seg = 128.0 * tps["bvh_nodes"] + 48.0 * (tps["triangle"] - float(st_last["n_loose_triangles"])) + 2 * 76.0 + 44.0
+            gbs = seg_total / max(world, 1) / args.steps * bytes_per_seg / (kernel_ms_last * 1e-3) * 1e-9 if kernel_ms_last > 0 else None
+            hbm = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"] if gbs else None,
+                   "bytes_per_segment": bytes_per_seg,
+                   "note": "upper bound on DRAM traffic: the BVH is L2-resident (ncu: lts hit rate ~80 %), so this path is not HBM bound"}
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
         fp32_peak = sms * 128 * peaks["sm_max_mhz"] * 1e6 * 1e-12          # T lane-ops/s, un-fused (FMA is barred by parity)
         seg_per_gpu = seg_total / max(world, 1) / args.steps
@@ -343,6 +352,7 @@ def main():
                          "kernel": dominant, "flops_per_segment": flops_per_seg, "tests_per_segment": tps, "kernel_ms": kernel_ms_last,
                          "peak_source": f"SMs({sms}) x 128 lanes x sm_max_mhz({peaks['sm_max_mhz']}) from MEASURED_PEAKS.json ({peaks['source']}); "
                                         "no tensor or HBM bound applies: scene and path state live in shared memory / registers"},
+            "roofline_hbm": hbm,
             "cpu_baseline": ({"value": cpu["mpaths_s"], "unit": "Mpaths/s", "cores": cpu["threads"], "kind": "port",
                               "sample": cpu["sample"], "mray_segments_per_s": cpu["mseg_s"]} if cpu else None),
         }

@@ -5,12 +5,14 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/ptb.h"
@@ -68,7 +70,31 @@ int main(int argc, char **argv) {
                 (unsigned long long)desc->n_objects, spp, width, res_y);
     std::vector<float> img((size_t)width * res_y * 3);
     auto t0 = std::chrono::steady_clock::now();
-    int rc = ptb_render(ctx, width, res_y, 0, spp, seed, PTB_OUT_MEAN, img.data(), nullptr, nullptr);
+    // progress line with elapsed / estimated total time, like the reference's print_progress (cmd_render.rs:54-80)
+    volatile uint64_t samples_done = 0;
+    std::atomic<bool> finished{false};
+    const double total = (double)width * res_y * (double)spp;
+    auto fmt = [](double s, char *buf, size_t n) {
+        unsigned long long t = (unsigned long long)s, h = t / 3600, m = (t / 60) % 60, sec = t % 60;
+        if (h == 0) std::snprintf(buf, n, "%llum:%02llus", m, sec);
+        else std::snprintf(buf, n, "%llu:%02llu:%02llu", h, m, sec);
+    };
+    std::thread progress([&]() {
+        while (!finished.load()) {
+            std::this_thread::sleep_for(std::chrono::milliseconds(500));
+            const double frac = (double)samples_done / total;
+            if (frac <= 0.0 || finished.load()) continue;
+            const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            char a[32], b[32];
+            fmt(el, a, sizeof a); fmt(el / frac, b, sizeof b);
+            std::printf("\rRendering ... %5.1f%% (%s / %s)", 100.0 * frac, a, b);
+            std::fflush(stdout);
+        }
+    });
+    int rc = ptb_render(ctx, width, res_y, 0, spp, seed, PTB_OUT_MEAN, img.data(), nullptr, &samples_done);
+    finished.store(true);
+    progress.join();
+    if (samples_done) std::printf("\n");
     double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (rc < 0) { std::fprintf(stderr, "error: %s\n", ptb_last_error(ctx)); return 2; }
     ptb_stats st;

@@ -363,3 +363,29 @@ def test_peer_memory_frame_single_rank(be):
         assert np.array_equal(bits(img), bits(O.resolve(osc.render_sum(W, H, spp, seed=8)[0], spp)))
     finally:
         frame.close()
+
+
+def test_checkpoint_resume_is_bit_identical(be):
+    """The fp32 sum framebuffer + the number of samples done is a checkpoint: accumulating the remaining
+    samples into it later gives the same bits as one uninterrupted render, because the per-pixel sum stays in sample order."""
+    import path_tracer_rust_b200 as P
+    import path_tracer_rust_b200.api as A
+    W, H = 80, 52
+    for sid, integ in (("cornell", 1), ("cornell", 2), ("mesh", 0)):
+        be.set_option("integrator", integ)
+        be.upload_scene(P.Scene.load(sid))
+        full = be.render(W, H, 11, seed=6, out_kind=A.PTB_OUT_SUM)
+        fb = be.device_alloc(W * H * 12)
+        try:
+            be.device_memset(fb, 0, W * H * 12)
+            be.render_device(W, H, 4, fb, spp_begin=0, seed=6, sync=True)
+            ckpt = np.empty((W * H, 3), f32)
+            be.device_to_host(ckpt, fb)                      # "save"
+            assert np.array_equal(bits(ckpt), bits(be.render(W, H, 4, seed=6, out_kind=A.PTB_OUT_SUM)))
+            be.render_device(W, H, 7, fb, spp_begin=4, seed=6, sync=True)   # "resume"
+            got = np.empty((W * H, 3), f32)
+            be.device_to_host(got, fb)
+            assert np.array_equal(bits(got), bits(full)), (sid, integ)
+        finally:
+            be.device_free(fb)
+    be.set_option("integrator", 0)

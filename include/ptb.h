@@ -117,7 +117,9 @@ int ptb_get_stats(const ptb_ctx *ctx, ptb_stats *out);
  *   "bvh_min_tris"    meshes with at least this many triangles are traversed through the BVH (default 24; a huge value = brute force)
  *   "bvh_min_spheres" scenes with at least this many spheres put them in the BVH (default 48)
  *   "integrator"      0 = auto (wavefront when the scene has a BVH, else megakernel), 1 = megakernel, 2 = wavefront
- *   "wavefront_paths" ray segments in flight per wavefront batch (default 2^23) */
+ *   "wavefront_paths" ray segments in flight per wavefront batch (default 2^23)
+ *   "bvh_leaf_max" (1..8, default 2), "wf_refill", "wf_descend_min", "wf_coop" (experimental four-lanes-per-ray trace kernel,
+ *   default 0): traversal tuning, see DESIGN.md */
 int ptb_set_option(ptb_ctx *ctx, const char *key, double value);
 /* Device self-test: the kernels' own correctly-rounded reciprocal (MUFU.RCP + 2 FFMA, no range check) is compared with
  * __frcp_rn over every float whose exponent field is in [1, 252]; *mismatches must come back 0. */

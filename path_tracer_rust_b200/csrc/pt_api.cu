@@ -74,7 +74,7 @@ struct ptb_ctx {
     WfWorkspace wf;
     int integrator = 0;             // 0 = auto (wavefront when the scene has a BVH), 1 = megakernel, 2 = wavefront
     double wavefront_paths = 8388608.0;  // ray segments in flight per wavefront batch
-    int wf_refill = 8, wf_descend_min = 12;
+    int wf_refill = 8, wf_descend_min = 12, wf_coop = 0;  // wf_coop: experimental four-lanes-per-ray trace kernel (slower)
     DevBuf<float> fb, scratch_f;
     DevBuf<int> scratch_i;
     DevBuf<int> tile_counter;
@@ -379,6 +379,7 @@ extern "C" int ptb_set_option(ptb_ctx *ctx, const char *key, double value) {
     else if (k == "bvh_leaf_max") ctx->bvh_opt.leaf_max = (int)value;
     else if (k == "wf_refill") ctx->wf_refill = (int)value;
     else if (k == "wf_descend_min") ctx->wf_descend_min = (int)value;
+    else if (k == "wf_coop") ctx->wf_coop = (int)value;
     else if (k == "integrator") ctx->integrator = (int)value;
     else if (k == "wavefront_paths") ctx->wavefront_paths = std::max(1024.0, value);
     else return fail(ctx, PTB_ERR_ARG, "ptb_set_option: unknown key " + k);
@@ -446,7 +447,7 @@ extern "C" int ptb_render_device(ptb_ctx *ctx, int width, int height, uint64_t s
         const bool small_image = a.n_tiles < 2 * ctx->sm_count * (RENDER_MIN_BLOCKS * RENDER_THREADS / 32);
         const bool wavefront = ctx->integrator == 2 || (ctx->integrator == 0 && (ctx->ds.bvh_root != BVH_EMPTY_REF || small_image));
         if (wavefront) {
-            CU(ctx, wavefront_render(ctx->ds, a, ctx->wf, ctx->sm_count, (size_t)ctx->wavefront_paths, ctx->wf_refill, ctx->wf_descend_min, st, &ctx->stats.kernel_launches));
+            CU(ctx, wavefront_render(ctx->ds, a, ctx->wf, ctx->sm_count, (size_t)ctx->wavefront_paths, ctx->wf_refill, ctx->wf_descend_min, ctx->wf_coop, st, &ctx->stats.kernel_launches));
         } else {
             CU(ctx, cudaMemsetAsync(ctx->tile_counter.p, 0, sizeof(int), st));
             CU(ctx, launch_render(ctx->ds, a, ctx->sm_count, st));

@@ -10,8 +10,10 @@
 // Mesh hits additionally need the mesh's bounding-sphere gate to pass (mod.rs:267-277); it is evaluated lazily, only
 // when a triangle would become the best hit, and cached per object.
 //
-// Node = 128 bytes = 8 x float4, four children in SoA form (one cache line, fetched with seven 16-byte loads):
-//   lo.x[4], lo.y[4], lo.z[4], hi.x[4], hi.y[4], hi.z[4], ref[4] (int bits), unused
+// Node = 128 bytes = 8 x float4 (one cache line), four children, child-major:
+//   [c]     = (lo.x, lo.y, lo.z, hi.x) of child c        [4 + c] = (hi.y, hi.z, ref as int bits, -) of child c
+// A single lane fetches it with four 256-bit loads; a sub-warp of four lanes (cooperative trace kernel) with two coalesced
+// 64-byte accesses, lane c taking child c.
 // A node has two to four children, packed from slot 0; an unused slot carries ref = BVH_EMPTY_REF.
 // ref >= 0: inner node index;  ref < 0: leaf, ~ref = (first_prim << 3) | (count - 1), prims contiguous in bvh_tri.
 // Primitive record = (A | obj), (E1 | tri) in bvh_tri (32 bytes, one 256-bit load) + (E2 | prio) in bvh_sph; a sphere is
@@ -75,13 +77,12 @@ __device__ __forceinline__ void cswap(float &ta, int &ra, float &tb, int &rb) {
 #define PTB_BVH_NODE_STEP()                                                                                      \
     do {                                                                                                         \
         const float4 *nd_ = sc.bvh_nodes + 8 * (size_t)cur;                                                      \
-        const F8 n01_ = ld256(nd_), n23_ = ld256(nd_ + 2), n45_ = ld256(nd_ + 4), n67_ = ld256(nd_ + 6);         \
-        const float4 lx_ = n01_.a, ly_ = n01_.b, lz_ = n23_.a, hx_ = n23_.b, hy_ = n45_.a, hz_ = n45_.b, rf_ = n67_.a; \
-        float t0_ = slab_t(lx_.x, ly_.x, lz_.x, hx_.x, hy_.x, hz_.x, id, ood, best.t);                           \
-        float t1_ = slab_t(lx_.y, ly_.y, lz_.y, hx_.y, hy_.y, hz_.y, id, ood, best.t);                           \
-        float t2_ = slab_t(lx_.z, ly_.z, lz_.z, hx_.z, hy_.z, hz_.z, id, ood, best.t);                           \
-        float t3_ = slab_t(lx_.w, ly_.w, lz_.w, hx_.w, hy_.w, hz_.w, id, ood, best.t);                           \
-        int r0_ = __float_as_int(rf_.x), r1_ = __float_as_int(rf_.y), r2_ = __float_as_int(rf_.z), r3_ = __float_as_int(rf_.w); \
+        const F8 a01_ = ld256(nd_), a23_ = ld256(nd_ + 2), b01_ = ld256(nd_ + 4), b23_ = ld256(nd_ + 6);         \
+        float t0_ = slab_t(a01_.a.x, a01_.a.y, a01_.a.z, a01_.a.w, b01_.a.x, b01_.a.y, id, ood, best.t);         \
+        float t1_ = slab_t(a01_.b.x, a01_.b.y, a01_.b.z, a01_.b.w, b01_.b.x, b01_.b.y, id, ood, best.t);         \
+        float t2_ = slab_t(a23_.a.x, a23_.a.y, a23_.a.z, a23_.a.w, b23_.a.x, b23_.a.y, id, ood, best.t);         \
+        float t3_ = slab_t(a23_.b.x, a23_.b.y, a23_.b.z, a23_.b.w, b23_.b.x, b23_.b.y, id, ood, best.t);         \
+        int r0_ = __float_as_int(b01_.a.z), r1_ = __float_as_int(b01_.b.z), r2_ = __float_as_int(b23_.a.z), r3_ = __float_as_int(b23_.b.z); \
         const float inf_ = __int_as_float(0x7f800000);                                                           \
         /* a node has two to four children; the slab test cannot reject an empty slot by itself */               \
         if (r2_ == BVH_EMPTY_REF) t2_ = inf_;                                                                    \

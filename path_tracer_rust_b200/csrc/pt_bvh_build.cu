@@ -208,14 +208,10 @@ __global__ void k_emit_nodes4(int n_inner, const int *__restrict__ alive, const 
         }
     }
     float4 *o = out + 8 * (size_t)new4[i];
-    o[0] = make_float4(lo[0].x, lo[1].x, lo[2].x, lo[3].x);
-    o[1] = make_float4(lo[0].y, lo[1].y, lo[2].y, lo[3].y);
-    o[2] = make_float4(lo[0].z, lo[1].z, lo[2].z, lo[3].z);
-    o[3] = make_float4(hi[0].x, hi[1].x, hi[2].x, hi[3].x);
-    o[4] = make_float4(hi[0].y, hi[1].y, hi[2].y, hi[3].y);
-    o[5] = make_float4(hi[0].z, hi[1].z, hi[2].z, hi[3].z);
-    o[6] = make_float4(__int_as_float(ref[0]), __int_as_float(ref[1]), __int_as_float(ref[2]), __int_as_float(ref[3]));
-    o[7] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = 0; c < 4; ++c) {  // child-major: a sub-warp of four lanes fetches a node with two coalesced 64-byte accesses
+        o[c] = make_float4(lo[c].x, lo[c].y, lo[c].z, hi[c].x);
+        o[4 + c] = make_float4(hi[c].y, hi[c].z, __int_as_float(ref[c]), 0.f);
+    }
 }
 
 __global__ void k_gather_prims(const float4 *__restrict__ recs, const int *__restrict__ idx, int n, float4 *__restrict__ out_ae,

@@ -144,6 +144,181 @@ __global__ void __launch_bounds__(WF_THREADS, 3) k_wf_trace(const DScene sc, con
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Cooperative trace kernel: FOUR LANES PER RAY, eight rays per warp.
+//
+// Why: with one lane per ray every diverged lane pays one L1 data-pipe wavefront per 16 bytes it loads (a 128-byte node = 8),
+// and ncu shows that pipe 90 % busy (profiles/r01d).  Here lane c of a sub-warp owns child c of the four-wide node: the four
+// lanes fetch the node with two coalesced 64-byte accesses (2 wavefronts instead of 8), each runs ONE slab test, the entry
+// distances are exchanged with three shuffles, every lane computes its child's rank, the nearest child becomes the next node and
+// the other hit children are pushed far-to-near, in parallel, onto the sub-warp's stack in shared memory.  In a leaf, lane c
+// tests primitive c (a leaf holds at most four) and the best candidate is found with two shuffle steps.  Only eight rays share
+// an instruction stream, so far fewer lanes wait for the slowest ray of the warp.
+// Arithmetic per primitive, prio tie-break and the lazy mesh gate are those of the one-lane-per-ray traversal: same hits.
+//
+// MEASURED (B200, synthetic scene, 1080p x 8 spp): bit-identical images, 2 wavefronts per node visit as designed, but 75 vs 175
+// Mpaths/s: with eight instead of ~26 rays per warp and the same 32 warps per SM there are three times fewer independent rays
+// in flight, and the traversal is latency bound.  Kept behind the option "wf_coop" (default off) as a tested experiment.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int WF_CSTACK = 32;  // shared-memory stack entries per ray; deeper entries go to a global overflow area
+
+__global__ void __launch_bounds__(WF_THREADS, 4) k_wf_trace_coop(const DScene sc, const WfQueue q, const int *__restrict__ n_rays_ptr,
+                                                                  int *__restrict__ fetch_ptr, unsigned long long *__restrict__ counters,
+                                                                  int2 *__restrict__ overflow, const int refill_groups) {
+    __shared__ int2 s_stack[WF_CSTACK * (WF_THREADS / 4)];
+    const int n = *n_rays_ptr;
+    const int lane = threadIdx.x & 31, sub = lane & 3, gbase = lane & ~3;
+    const unsigned gmask = 0xFu << gbase;
+    const int group_in_block = threadIdx.x >> 2;
+    int2 *const ovf = overflow + ((size_t)blockIdx.x * (WF_THREADS / 4) + group_in_block) * BVH_STACK;
+#define PTB_CSTK(i) (*((i) < WF_CSTACK ? &s_stack[(i) * (WF_THREADS / 4) + group_in_block] : &ovf[(i) - WF_CSTACK]))
+    const float inf = __int_as_float(0x7f800000);
+    unsigned n_nodes = 0, n_prims = 0;
+
+    bool busy = false, exhausted = false;  // busy / cur / sp / best are uniform within a sub-warp
+    int w_next = 0, w_end = 0;
+    int ray_idx = 0;
+    V3 o = mk3(0.f, 0.f, 0.f), d = mk3(0.f, 0.f, 1.f), id = mk3(1.f, 1.f, 1.f), ood = mk3(0.f, 0.f, 0.f);
+    Hit best;
+    best.t = 0.f; best.prio = PRIO_NONE; best.ref = REF_NONE;
+    int cur = BVH_EMPTY_REF, sp = 0, gate_obj = -1;
+    bool gate_pass = false;
+
+#define PTB_CPOP()                                                          \
+    do {                                                                    \
+        cur = BVH_EMPTY_REF;                                                \
+        while (sp > 0) {                                                    \
+            --sp;                                                           \
+            const int2 e_ = PTB_CSTK(sp);                                   \
+            if (__int_as_float(e_.y) <= best.t) { cur = e_.x; break; }      \
+        }                                                                   \
+    } while (0)
+
+    for (;;) {
+        const unsigned busy_mask = __ballot_sync(0xffffffffu, busy);         // four equal bits per sub-warp
+        const int n_idle = (32 - __popc(busy_mask)) >> 2;                    // idle sub-warps
+        if (!exhausted && (n_idle >= refill_groups || busy_mask == 0u)) {
+            if (w_next >= w_end) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(fetch_ptr, WF_CHUNK);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                w_next = base;
+                w_end = min(base + WF_CHUNK, n);
+                if (base >= n) exhausted = true;
+            }
+            // rank of this sub-warp among the idle ones: idle sub-warps below it (count one bit per sub-warp)
+            const unsigned idle_leaders = ~busy_mask & 0x11111111u;
+            const int idx = w_next + __popc(idle_leaders & ((1u << gbase) - 1u));
+            const bool got = !busy && idx < w_end;
+            w_next = min(w_next + n_idle, w_end);
+            if (got) {
+                const float4 qo = __ldcs(&q.o[idx]), qd = __ldcs(&q.d[idx]);
+                o = mk3(qo.x, qo.y, qo.z); d = mk3(qd.x, qd.y, qd.z);
+                ray_idx = idx;
+                best.t = __ldcs(&q.hit_t[idx]); best.ref = __ldcs(&q.hit_ref[idx]); best.prio = __ldcs(&q.hit_prio[idx]);
+                id = mk3(safe_rcp_dir(d.x), safe_rcp_dir(d.y), safe_rcp_dir(d.z));
+                ood = mk3(o.x * id.x, o.y * id.y, o.z * id.z);
+                cur = sc.bvh_root; sp = 0; gate_obj = -1;
+                busy = true;
+            }
+        }
+        if (__ballot_sync(0xffffffffu, busy) == 0u) break;
+        if (busy) {
+            while (cur >= 0) {  // ---- inner node: lane `sub` owns child `sub`
+                const float4 *nd = sc.bvh_nodes + 8 * (size_t)cur;
+                const float4 ca = __ldg(nd + sub), cb = __ldg(nd + 4 + sub);
+                const int ref = __float_as_int(cb.z);
+                float t_in;
+                const bool hit = ref != BVH_EMPTY_REF && slab(ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, id, ood, best.t, t_in);
+                const float t = hit ? t_in : inf;
+                // rank of my child among the hit children (ties by child index)
+                int rank = 0;
+#pragma unroll
+                for (int j = 1; j < 4; ++j) {
+                    const float tj = __shfl_sync(gmask, t, gbase + ((sub + j) & 3));
+                    const int cj = (sub + j) & 3;
+                    rank += (tj < t || (tj == t && cj < sub)) ? 1 : 0;
+                }
+                const unsigned hits = (__ballot_sync(gmask, hit) >> gbase) & 0xFu;
+                const int n_hit = __popc(hits);
+                if (sub == 0) n_nodes++;
+                if (n_hit == 0) {
+                    PTB_CPOP();
+                } else {
+                    // the nearest child is followed, the others are postponed far-to-near (the nearest of them ends on top)
+                    if (hit && rank > 0) PTB_CSTK(sp + (n_hit - 1 - rank)) = make_int2(ref, __float_as_int(t));
+                    const unsigned first = __ballot_sync(gmask, hit && rank == 0);
+                    cur = __shfl_sync(gmask, ref, __ffs(first) - 1);
+                    sp += n_hit - 1;
+                    __syncwarp(gmask);  // the pushes must be visible to the sub-warp's later pops
+                }
+                if ((__popc(__activemask()) >> 2) < 3) break;  // few rays still descending: let the leaf holders get on with it
+            }
+            if (cur < 0 && cur != BVH_EMPTY_REF) {  // ---- leaf: lane `sub` owns primitive `sub`
+                const int code = ~cur;
+                const int first = code >> 3, count = (code & 7) + 1;
+                if (sub == 0) n_prims += count;
+                float ct = inf;
+                uint32_t cprio = PRIO_NONE;
+                int cref = REF_NONE;
+                for (int k0 = 0; k0 < count; k0 += 4) {  // leaves hold at most four primitives by construction; stay general
+                    const int k = first + k0 + sub;
+                    if (k0 + sub < count) {
+                        const float4 A = __ldg(&sc.bvh_tri[2 * (size_t)k]), E1 = __ldg(&sc.bvh_tri[2 * (size_t)k + 1]), E2 = __ldg(&sc.bvh_sph[k]);
+                        const bool is_sphere = __float_as_int(E1.w) < 0;
+                        float tt;
+                        if (is_sphere) tt = sphere_t(xyz(A), E1.x, o, d);
+                        else tt = triangle_t(xyz(A), xyz(E1), xyz(E2), o, d);
+                        const uint32_t prio = (uint32_t)__float_as_int(E2.w);
+                        const bool beats_best = tt < best.t || (tt == best.t && prio < best.prio);
+                        const bool beats_mine = tt < ct || (tt == ct && prio < cprio);
+                        if (tt > 0.0f && beats_best && beats_mine) {
+                            bool ok = true;
+                            if (!is_sphere) {  // mesh gate (mod.rs:267-277), lazily, cached per lane and object
+                                const int obj = __float_as_int(A.w);
+                                if (obj != gate_obj) {
+                                    const float4 g = __ldg(&sc.obj_gate[obj]);
+                                    gate_pass = sphere_gate(xyz(g), g.w, o, d);
+                                    gate_obj = obj;
+                                }
+                                ok = gate_pass;
+                            }
+                            if (ok) { ct = tt; cprio = prio; cref = REF_BVH_BIT | (is_sphere ? REF_SPHERE_BIT : 0) | k; }
+                        }
+                    }
+                }
+                // best candidate of the sub-warp (t, then prio), two butterfly steps
+#pragma unroll
+                for (int m = 1; m <= 2; m <<= 1) {
+                    const float ot = __shfl_xor_sync(gmask, ct, m);
+                    const uint32_t op = __shfl_xor_sync(gmask, cprio, m);
+                    const int orf = __shfl_xor_sync(gmask, cref, m);
+                    if (ot < ct || (ot == ct && op < cprio)) { ct = ot; cprio = op; cref = orf; }
+                }
+                if (cref != REF_NONE) { best.t = ct; best.prio = cprio; best.ref = cref; }
+                PTB_CPOP();
+            }
+            if (cur == BVH_EMPTY_REF) {
+                if (sub == 0) {
+                    __stcs(&q.hit_t[ray_idx], best.t);
+                    __stcs(&q.hit_ref[ray_idx], best.ref);
+                }
+                busy = false;
+            }
+        }
+    }
+#undef PTB_CPOP
+#undef PTB_CSTK
+    for (int off = 16; off > 0; off >>= 1) {
+        n_nodes += __shfl_down_sync(0xffffffffu, n_nodes, off);
+        n_prims += __shfl_down_sync(0xffffffffu, n_prims, off);
+    }
+    if (lane == 0 && (n_nodes | n_prims)) {
+        atomicAdd(&counters[1], (unsigned long long)n_nodes);
+        atomicAdd(&counters[2], (unsigned long long)n_prims);
+    }
+}
+
 // material arm of every queued segment; appends the next bounce
 __global__ void __launch_bounds__(256) k_wf_shade(const DScene sc, const WfQueue q, const int *__restrict__ n_rays_ptr, WfQueue nq,
                                                   int *__restrict__ n_next_ptr, float4 *__restrict__ slots, unsigned long long n_paths,
@@ -256,6 +431,7 @@ void wf_release(WfWorkspace &w) {
     }
     if (w.slots) cudaFree(w.slots);
     if (w.counters) cudaFree(w.counters);
+    if (w.overflow) cudaFree(w.overflow);
     w = WfWorkspace{};
 }
 
@@ -281,7 +457,7 @@ static cudaError_t wf_reserve(WfWorkspace &w, size_t n_paths) {
 
 // renders samples [a.spp_begin, a.spp_begin + a.spp_count) of every pixel into a.sum_rgb; returns the number of kernels launched
 cudaError_t wavefront_render(const DScene &sc, const RenderArgs &a, WfWorkspace &w, int sm_count, size_t target_paths, int refill,
-                             int descend_min, cudaStream_t st,
+                             int descend_min, int coop, cudaStream_t st,
                              unsigned *launches) {
     const unsigned npix = (unsigned)a.width * (unsigned)a.height;
     unsigned K = (unsigned)std::max<size_t>(1, target_paths / npix);
@@ -297,7 +473,19 @@ cudaError_t wavefront_render(const DScene &sc, const RenderArgs &a, WfWorkspace 
     int trace_per_sm = 0;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_per_sm, k_wf_trace, WF_THREADS, 0)) != cudaSuccess) return e;
     if (trace_per_sm < 1) return cudaErrorLaunchOutOfResources;
-    const int trace_blocks = sm_count * trace_per_sm, wide_blocks = sm_count * 8;
+    int coop_per_sm = 0;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&coop_per_sm, k_wf_trace_coop, WF_THREADS, 0)) != cudaSuccess) return e;
+    if (coop_per_sm < 1) return cudaErrorLaunchOutOfResources;
+    const int trace_blocks = sm_count * trace_per_sm, coop_blocks = sm_count * coop_per_sm, wide_blocks = sm_count * 8;
+    if (coop) {
+        const size_t need = (size_t)coop_blocks * (WF_THREADS / 4) * BVH_STACK;
+        if (w.cap_overflow < need) {
+            if (w.overflow) cudaFree(w.overflow);
+            w.overflow = nullptr; w.cap_overflow = 0;
+            if ((e = cudaMalloc((void **)&w.overflow, need * sizeof(int2))) != cudaSuccess) return e;
+            w.cap_overflow = need;
+        }
+    }
 
     unsigned long long done = 0;
     while (done < a.spp_count) {
@@ -313,7 +501,11 @@ cudaError_t wavefront_render(const DScene &sc, const RenderArgs &a, WfWorkspace 
         (*launches)++;
         for (int b = 0; b < WF_MAX_BOUNCES; ++b) {
             const WfQueue &cur = w.q[b & 1], &nxt = w.q[(b + 1) & 1];
-            k_wf_trace<<<trace_blocks, WF_THREADS, 0, st>>>(sc, cur, w.counters + 2 * b, w.counters + 2 * b + 1, a.segment_counter, refill, descend_min);
+            if (coop)
+                k_wf_trace_coop<<<coop_blocks, WF_THREADS, 0, st>>>(sc, cur, w.counters + 2 * b, w.counters + 2 * b + 1, a.segment_counter,
+                                                                     w.overflow, 2);
+            else
+                k_wf_trace<<<trace_blocks, WF_THREADS, 0, st>>>(sc, cur, w.counters + 2 * b, w.counters + 2 * b + 1, a.segment_counter, refill, descend_min);
             k_wf_shade<<<wide_blocks, 256, smem, st>>>(sc, cur, w.counters + 2 * b, nxt, w.counters + 2 * (b + 1), w.slots,
                                                        n_paths, npix, s0, a.seed, a.segment_counter);
             *launches += 2;

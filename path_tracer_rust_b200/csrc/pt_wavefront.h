@@ -27,12 +27,14 @@ struct WfWorkspace {
     WfQueue q[2];
     float4 *slots = nullptr;  // [4 branches][n_paths] finished branch sums
     int *counters = nullptr;  // per bounce: queue length, fetch cursor
+    int2 *overflow = nullptr; // cooperative trace kernel: stack entries beyond the shared-memory part, per sub-warp
+    size_t cap_overflow = 0;
     size_t cap_paths = 0;
 };
 
 void wf_release(WfWorkspace &w);
 cudaError_t wavefront_render(const DScene &sc, const RenderArgs &a, WfWorkspace &w, int sm_count, size_t target_paths, int refill,
-                             int descend_min, cudaStream_t st,
+                             int descend_min, int coop, cudaStream_t st,
                              unsigned *launches);
 
 }  // namespace ptb

@@ -65,7 +65,8 @@ __global__ void __launch_bounds__(256) k_wf_generate(const DScene sc, int W, int
 }
 
 // closest hit of every queued segment
-__global__ void __launch_bounds__(WF_THREADS, 3) k_wf_trace(const DScene sc, const WfQueue q, const int *__restrict__ n_rays_ptr,
+// (measured: 5 or 6 CTAs per SM with the spills that takes, or prefetching the leaf while a lane waits, are all slower or neutral)
+__global__ void __launch_bounds__(WF_THREADS, 4) k_wf_trace(const DScene sc, const WfQueue q, const int *__restrict__ n_rays_ptr,
                                                              int *__restrict__ fetch_ptr, unsigned long long *__restrict__ counters,
                                                              const int wf_refill, const int wf_descend_min) {
     const int n = *n_rays_ptr;

@@ -204,8 +204,21 @@ def main():
     be = P.Backend(local_rank)
     be.upload_scene(scene)
     use_peer = world > 1 and args.reduce == "peer"
+    frame = None
+    if use_peer:
+        # CUDA IPC needs every rank to see every peer; if any rank cannot set it up, all ranks fall back to the NCCL reduce
+        ok = 1
+        try:
+            frame = PeerMemoryFrame(be, W, H, seed=2026, rank=rank, world_size=world)
+        except Exception as exc:  # noqa: BLE001
+            print(f"[rank {rank}] peer-memory frame unavailable ({exc}); falling back to NCCL", file=sys.stderr, flush=True)
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            frame = None
+            use_peer = False
     shard = CudaShardRenderer(be, W, H, seed=2026, device=dev) if not use_peer else None
-    frame = PeerMemoryFrame(be, W, H, seed=2026, rank=rank, world_size=world) if use_peer else None
     nfl = W * H * 3
     host_img = torch.empty(nfl, dtype=torch.float32).pin_memory() if rank == 0 else None
     l2_flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)

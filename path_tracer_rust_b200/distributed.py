@@ -81,32 +81,66 @@ class PeerMemoryFrame:
     """
 
     def __init__(self, backend, width: int, height: int, seed: int, rank: int, world_size: int, group=None, dst: int = 0):
+        """Collective over `group`: either every rank ends up with a working frame or every rank raises BackendError."""
         import torch.distributed as dist
+        from .api import BackendError
         self.be, self.W, self.H, self.seed = backend, width, height, seed
         self.rank, self.world, self.group, self.dst, self.dist = rank, world_size, group, dst, dist
         self.n_floats = width * height * 3
-        self.fb = backend.device_alloc(self.n_floats * 4)
-        self.out = backend.device_alloc(self.n_floats * 4) if rank == dst else 0
-        mine = {"fb": backend.ipc_export(self.fb), "out": backend.ipc_export(self.out) if rank == dst else None}
-        handles = [None] * world_size
-        if world_size > 1:
-            dist.all_gather_object(handles, mine, group=group)
-        else:
-            handles = [mine]
+        self.fb = self.out = 0
+        self._opened, self.peer_fb, self.dst_out = [], [], 0
+
+        def agree(value):  # every rank learns every rank's value (None = that rank failed)
+            if world_size == 1:
+                return [value]
+            got = [None] * world_size
+            dist.all_gather_object(got, value, group=group)
+            return got
+
+        mine, err = None, None
+        try:
+            self.fb = backend.device_alloc(self.n_floats * 4)
+            self.out = backend.device_alloc(self.n_floats * 4) if rank == dst else 0
+            mine = {"fb": backend.ipc_export(self.fb), "out": backend.ipc_export(self.out) if rank == dst else None}
+        except Exception as exc:  # noqa: BLE001
+            err = exc
+        handles = agree(mine)
+        ok = all(h is not None for h in handles)
+        if ok:
+            try:
+                for g, h in enumerate(handles):
+                    if g == rank:
+                        self.peer_fb.append(self.fb)
+                    else:
+                        p = backend.ipc_open(h["fb"])
+                        self._opened.append(p)
+                        self.peer_fb.append(p)
+                if rank == dst:
+                    self.dst_out = self.out
+                else:
+                    self.dst_out = backend.ipc_open(handles[dst]["out"])
+                    self._opened.append(self.dst_out)
+            except Exception as exc:  # noqa: BLE001
+                err = exc
+        ok = all(agree(err is None))
+        if not ok:
+            self._release_local()
+            raise BackendError(-2, f"peer-memory frame could not be set up on every rank (rank {rank}: {err})")
+
+    def _release_local(self):
+        for p in self._opened:
+            try:
+                self.be.ipc_close(p)
+            except Exception:  # noqa: BLE001
+                pass
         self._opened = []
-        self.peer_fb = []
-        for g, h in enumerate(handles):
-            if g == rank:
-                self.peer_fb.append(self.fb)
-            else:
-                p = backend.ipc_open(h["fb"])
-                self._opened.append(p)
-                self.peer_fb.append(p)
-        if rank == dst:
-            self.dst_out = self.out
-        else:
-            self.dst_out = backend.ipc_open(handles[dst]["out"])
-            self._opened.append(self.dst_out)
+        for p in (self.fb, self.out):
+            if p:
+                try:
+                    self.be.device_free(p)
+                except Exception:  # noqa: BLE001
+                    pass
+        self.fb = self.out = 0
 
     def _barrier(self):
         if self.world > 1:
@@ -137,7 +171,5 @@ class PeerMemoryFrame:
         for p in self._opened:
             self.be.ipc_close(p)
         self._opened = []
-        self._barrier()
-        self.be.device_free(self.fb)
-        if self.out:
-            self.be.device_free(self.out)
+        self._barrier()       # nobody has a peer's buffer mapped any more: the owners may free
+        self._release_local()

@@ -389,3 +389,39 @@ def test_checkpoint_resume_is_bit_identical(be):
         finally:
             be.device_free(fb)
     be.set_option("integrator", 0)
+
+
+# ---- edge cases -------------------------------------------------------------------------------------------------------
+def test_edge_cases(be, kat_scene):
+    import path_tracer_rust_b200 as P
+    import path_tracer_rust_b200.api as A
+    # empty scene: every ray misses, the image is black, one segment per sample
+    path = kat_scene([], "empty")
+    sc, osc = load_both(be, path)
+    for integ in (1, 2):
+        be.set_option("integrator", integ)
+        be.upload_scene(sc)
+        img = be.render(17, 9, 3, seed=1, out_kind=A.PTB_OUT_SUM)
+        assert not img.any() and be.stats()["segments"] == 17 * 9 * 3
+        obj, tri, t = be.primary_hits(5, 3)
+        assert (obj == -1).all() and (tri == -1).all() and not t.any()
+    be.set_option("integrator", 0)
+    ofb, ost = osc.render_sum(17, 9, 3, seed=1)
+    assert not ofb.any() and int(ost[0]) == 17 * 9 * 3
+    # one pixel, one sample; zero rays; zero samples in SUM mode; widths that are not multiples of the 8x4 tile
+    sc, osc = load_both(be, "cornell")
+    for (W, H, spp) in ((1, 1, 1), (1, 7, 2), (9, 1, 3), (33, 5, 1)):
+        for integ in (1, 2):
+            be.set_option("integrator", integ)
+            g = be.render(W, H, spp, seed=2, out_kind=A.PTB_OUT_SUM)
+            o, _ = osc.render_sum(W, H, spp, seed=2)
+            assert np.array_equal(bits(g), bits(o)), (W, H, spp, integ)
+    be.set_option("integrator", 0)
+    assert not be.render(8, 8, 0, seed=2, out_kind=A.PTB_OUT_SUM).any()
+    r = be.intersect(np.zeros((0, 6), f32))
+    assert all(len(a) == 0 for a in r)
+    # large sample indices (beyond 2^32) keep working: the Philox counter carries the high word
+    big = (1 << 32) + 5
+    g = be.render(12, 8, 2, spp_begin=big, seed=3, out_kind=A.PTB_OUT_SUM)
+    o, _ = osc.render_sum(12, 8, 2, spp_begin=big, seed=3)
+    assert np.array_equal(bits(g), bits(o))

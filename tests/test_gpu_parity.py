@@ -425,3 +425,51 @@ def test_edge_cases(be, kat_scene):
     g = be.render(12, 8, 2, spp_begin=big, seed=3, out_kind=A.PTB_OUT_SUM)
     o, _ = osc.render_sum(12, 8, 2, spp_begin=big, seed=3)
     assert np.array_equal(bits(g), bits(o))
+
+
+def test_bvh_padding_holds_for_grazing_rays(synthetic_small):
+    """Worst case for the conservative box padding (pt_bvh_build.cu: triangle_pad): rays almost parallel to a triangle (|det| just
+    above the reference's 1e-4 cut-off, where the fp32 Moeller-Trumbore error is amplified by 1/det), aimed at its edges, started
+    far away.  The BVH must still return exactly what the brute-force scan returns."""
+    import ctypes as C
+    import path_tracer_rust_b200 as P
+    rng = np.random.default_rng(2024)
+    for path, base, far in ((scene_path("mesh"), None, 12.0), (synthetic_small[0], synthetic_small[1], 60.0)):
+        sc = P.Scene.load(path, base_dir=base)
+        d = sc._desc.contents
+        mesh = max(range(sc.n_objects), key=lambda i: d.objects[i].tri_count)
+        o = d.objects[mesh]
+        tris = np.frombuffer(C.string_at(d.triangles, 36 * sc.n_triangles), f32).reshape(-1, 3, 3)[o.tri_begin:o.tri_begin + o.tri_count]
+        tris = tris + np.array(list(o.position), f32)
+        n = 400_000
+        pick = rng.integers(0, len(tris), n)
+        A, E1, E2 = tris[pick, 0], tris[pick, 1] - tris[pick, 0], tris[pick, 2] - tris[pick, 0]
+        N = np.cross(E1, E2)
+        area2 = np.linalg.norm(N, axis=1, keepdims=True)
+        nrm = N / area2
+        # a point on or just outside an edge of the triangle
+        u = rng.choice([0.0, 1.0, 0.5], n) + rng.normal(scale=0.02, size=n)
+        v = rng.uniform(-0.02, 1.02, n) * (1 - np.clip(u, 0, 1))
+        Pnt = A + E1 * u[:, None] + E2 * v[:, None]
+        # in-plane direction plus just enough normal component for |det| = k * 1e-4, k in [0.5, 20]
+        phi = rng.uniform(0, 2 * np.pi, n)
+        e1n = E1 / np.linalg.norm(E1, axis=1, keepdims=True)
+        inpl = e1n * np.cos(phi)[:, None] + np.cross(nrm, e1n) * np.sin(phi)[:, None]
+        k = rng.uniform(0.5, 20.0, (n, 1)) * rng.choice([-1.0, 1.0], (n, 1))
+        dirs = inpl + nrm * (k * 1e-4 / area2)
+        dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+        dist = rng.uniform(0.05, far, (n, 1))
+        rays = np.concatenate([Pnt - dirs * dist, dirs], 1).astype(f32)
+        bvh, bf = P.Backend(0), P.Backend(0)
+        try:
+            bf.set_option("bvh_min_tris", 1e18)
+            bf.set_option("bvh_min_spheres", 1e18)
+            bvh.upload_scene(sc)
+            bf.upload_scene(sc)
+            assert bvh.stats()["n_bvh_triangles"] > 0 and bf.stats()["n_bvh_triangles"] == 0
+            a, b = bvh.intersect(rays), bf.intersect(rays)
+            _cmp(a, b)
+            assert (a[1] >= 0).sum() > n // 50          # the grazing hits really happen
+        finally:
+            bvh.close()
+            bf.close()

@@ -71,36 +71,64 @@ __global__ void __launch_bounds__(RENDER_THREADS, RENDER_MIN_BLOCKS) k_render(co
     const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
     unsigned long long n_segments = 0;
 
-    for (;;) {
-        int tile = 0;
-        if (lane == 0) tile = atomicAdd(a.tile_counter, 1);
-        tile = __shfl_sync(0xffffffffu, tile, 0);
-        if (tile >= a.n_tiles) break;
-        const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
-        const int px = tx * TILE_W + (lane & (TILE_W - 1)), row = ty * TILE_H + (lane / TILE_W);
-        const bool valid = px < W && row < H;
-        const uint32_t pixel = (uint32_t)row * (uint32_t)W + (uint32_t)px;
-        const int y = H - 1 - row;  // mod.rs:805
-        float *fb = a.sum_rgb + 3ull * pixel;
-        V3 acc = mk3(0.f, 0.f, 0.f);
-        if (valid) acc = mk3(fb[0], fb[1], fb[2]);
+    // Work distribution: pixels are enumerated tile-major (slot = tile * 32 + position inside the 8x4 tile) and handed out
+    // lane by lane from one global counter.  A lane that has used up its pixel's sample budget stores the sum and takes the next
+    // slot at once, so no lane waits for the slowest pixel of a tile.  One lane still owns one pixel at a time and walks its
+    // samples in order: the per-pixel fp32 sum keeps the reference's order (mod.rs:846).
+    const unsigned n_slots = (unsigned)a.n_tiles * 32u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const unsigned long long s_end = a.spp_begin + a.spp_count;
+    bool have_pixel = false, retired = false;
+    uint32_t pixel = 0;
+    int px = 0, y = 0;
+    float *fb = a.sum_rgb;
+    V3 acc = mk3(0.f, 0.f, 0.f);
+    // Camera rays are generated in batches: every lane keeps one spare primary direction, a lane that finishes a path
+    // just swaps it in, and the (long, otherwise badly diverged) ray-generation code runs only when REGEN_BATCH lanes
+    // need a new spare or some lane would have to idle.  Per-lane order of samples and of `acc += L` is unchanged.
+    unsigned long long s_next = a.spp_begin, s = a.spp_begin;
+    bool has_path = false, spare_ok = false;
+    V3 spare_d = mk3(0.f, 0.f, 1.f);
+    V3 o = mk3(0.f, 0.f, 0.f), d = mk3(0.f, 0.f, 1.f), T = mk3(1.f, 1.f, 1.f), L = mk3(0.f, 0.f, 0.f);
+    int depth = 0, sp = 0, code = 0;      // code: which refraction splits were left through the transmitted child
+    unsigned chain_mask = 1u;             // branches of the path tree that exist for this sample
+    uint32_t nseg = 0;
+    PathStackEntry stk[2];
+    V3 Lc[4];                             // finished branches' emission sums; radiance = ((L0+L1)+L2)+L3
 
-        // Camera rays are generated in batches: every lane keeps one spare primary direction, a lane that finishes a path
-        // just swaps it in, and the (long, otherwise badly diverged) ray-generation code runs only when REGEN_BATCH lanes
-        // need a new spare or some lane would have to idle.  Per-lane order of samples and of `acc += L` is unchanged.
-        unsigned long long s_next = a.spp_begin, s = a.spp_begin;
-        const unsigned long long s_end = a.spp_begin + a.spp_count;
-        bool has_path = false, spare_ok = false;
-        V3 spare_d = mk3(0.f, 0.f, 1.f);
-        V3 o = mk3(0.f, 0.f, 0.f), d = mk3(0.f, 0.f, 1.f), T = mk3(1.f, 1.f, 1.f), L = mk3(0.f, 0.f, 0.f);
-        int depth = 0, sp = 0, code = 0;      // code: which refraction splits were left through the transmitted child
-        unsigned chain_mask = 1u;             // branches of the path tree that exist for this sample
-        uint32_t nseg = 0;
-        PathStackEntry stk[2];
-        V3 Lc[4];                             // finished branches' emission sums; radiance = ((L0+L1)+L2)+L3
-
+    {
         for (;;) {
-            const bool need = valid && !spare_ok && s_next < s_end;
+            // a pixel whose samples are all done (no path in flight, no spare ray, budget used up) is written back
+            if (have_pixel && !has_path && !spare_ok && s_next >= s_end) {
+                fb[0] = acc.x; fb[1] = acc.y; fb[2] = acc.z;
+                have_pixel = false;
+            }
+            const unsigned want_mask = __ballot_sync(0xffffffffu, !have_pixel && !retired);
+            if (want_mask) {
+                const int leader = __ffs(want_mask) - 1;
+                unsigned base = 0;
+                if (lane == leader) base = (unsigned)atomicAdd(a.tile_counter, __popc(want_mask));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (!have_pixel && !retired) {
+                    const unsigned slot = base + __popc(want_mask & lt_mask);
+                    if (slot >= n_slots) retired = true;
+                    else {
+                        const int tile = (int)(slot >> 5), pos = (int)(slot & 31u);
+                        const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
+                        px = tx * TILE_W + (pos & (TILE_W - 1));
+                        const int row = ty * TILE_H + (pos / TILE_W);
+                        if (px < W && row < H && a.spp_count > 0) {  // (off-image slots of edge tiles are simply skipped)
+                            pixel = (uint32_t)row * (uint32_t)W + (uint32_t)px;
+                            y = H - 1 - row;  // mod.rs:805
+                            fb = a.sum_rgb + 3ull * pixel;
+                            acc = mk3(fb[0], fb[1], fb[2]);
+                            s_next = a.spp_begin;
+                            have_pixel = true;
+                        }
+                    }
+                }
+            }
+            const bool need = have_pixel && !spare_ok && s_next < s_end;
             const unsigned need_mask = __ballot_sync(0xffffffffu, need);
             const bool starving = __any_sync(0xffffffffu, need && !has_path);
             if (starving || __popc(need_mask) >= REGEN_BATCH) {
@@ -125,7 +153,10 @@ __global__ void __launch_bounds__(RENDER_THREADS, RENDER_MIN_BLOCKS) k_render(co
                 has_path = true;
             }
             const unsigned amask = __ballot_sync(0xffffffffu, has_path);
-            if (amask == 0u) break;
+            if (amask == 0u) {
+                if (__ballot_sync(0xffffffffu, have_pixel || !retired) == 0u) break;  // every lane is out of pixels
+                continue;
+            }
             if (has_path) {
                 uint32_t rnd[4];
                 // ---- one radiance() call (mod.rs:662): event (code<<4 | new_depth); slots 0 = RR, 1,2 = diffuse, 3 = refraction
@@ -172,7 +203,6 @@ __global__ void __launch_bounds__(RENDER_THREADS, RENDER_MIN_BLOCKS) k_render(co
                 }
             }
         }
-        if (valid) { fb[0] = acc.x; fb[1] = acc.y; fb[2] = acc.z; }
         n_segments += nseg;
     }
     // one atomic per warp

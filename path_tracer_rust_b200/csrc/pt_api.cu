@@ -293,7 +293,9 @@ extern "C" int ptb_upload_scene(ptb_ctx *ctx, const ptb_scene_desc *desc) {
             lobj.push_back(f4(ibits(0), ubits(prio_base[k]), ibits(0), ibits(static_cast<int32_t>(k))));
         } else {
             lobj.push_back(gate[k]);
-            lobj.push_back(f4(ibits(1), ibits(static_cast<int32_t>(ltri.size() / 3)), ibits(static_cast<int32_t>(o.tri_count)),
+            // gate shortcut (sphere_gate): usable for 0.4 <= r <= 1000, see the derivation there
+            const float r2_inside = (o.bs_radius >= 0.4f && o.bs_radius <= 1000.0f) ? (o.bs_radius * o.bs_radius) * 0.999f : -1.0f;
+            lobj.push_back(f4(r2_inside, ibits(static_cast<int32_t>(ltri.size() / 3)), ibits(static_cast<int32_t>(o.tri_count)),
                               ibits(static_cast<int32_t>(k))));
             const V3 off = v3(o.position);
             for (uint64_t j = 0; j < o.tri_count; ++j) {

@@ -29,7 +29,7 @@ __device__ __forceinline__ void closest_hit_loose(const float4 *__restrict__ s_o
             }
         } else {
             // mesh: bounding-sphere gate first (mod.rs:267-277); skip the triangle scan if no lane passes
-            const bool pass = sphere_gate(xyz(sph), sph.w, o, d);
+            const bool pass = sphere_gate(xyz(sph), sph.w, o, d, mb.x);  // for a mesh, mb.x carries r2_inside (never +0)
             if (__any_sync(amask, pass)) {
                 int k = __float_as_int(mb.y);
                 const int k1 = k + __float_as_int(mb.z);

@@ -74,6 +74,7 @@ struct ptb_ctx {
     WfWorkspace wf;
     int integrator = 0;             // 0 = auto (wavefront when the scene has a BVH), 1 = megakernel, 2 = wavefront
     double wavefront_paths = 8388608.0;  // ray segments in flight per wavefront batch
+    int regen_batch = REGEN_BATCH;
     int wf_refill = 8, wf_descend_min = 12, wf_coop = 0;  // wf_coop: experimental four-lanes-per-ray trace kernel (slower)
     DevBuf<float> fb, scratch_f;
     DevBuf<int> scratch_i;
@@ -382,6 +383,7 @@ extern "C" int ptb_set_option(ptb_ctx *ctx, const char *key, double value) {
     else if (k == "wf_refill") ctx->wf_refill = (int)value;
     else if (k == "wf_descend_min") ctx->wf_descend_min = (int)value;
     else if (k == "wf_coop") ctx->wf_coop = (int)value;
+    else if (k == "regen_batch") ctx->regen_batch = std::max(1, std::min(32, (int)value));
     else if (k == "integrator") ctx->integrator = (int)value;
     else if (k == "wavefront_paths") ctx->wavefront_paths = std::max(1024.0, value);
     else return fail(ctx, PTB_ERR_ARG, "ptb_set_option: unknown key " + k);
@@ -427,6 +429,7 @@ extern "C" int ptb_render_device(ptb_ctx *ctx, int width, int height, uint64_t s
     RenderArgs a{};
     a.width = width; a.height = height; a.seed = seed; a.sum_rgb = d_sum_rgb;
     a.tile_counter = ctx->tile_counter.p; a.segment_counter = ctx->seg_counter.p;
+    a.regen_batch = ctx->regen_batch;
     a.tiles_x = (width + TILE_W - 1) / TILE_W;
     a.n_tiles = a.tiles_x * ((height + TILE_H - 1) / TILE_H);
 

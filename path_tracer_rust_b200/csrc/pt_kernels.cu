@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, RENDER_MIN_BLOCKS) k_render(co
             const bool need = have_pixel && !spare_ok && s_next < s_end;
             const unsigned need_mask = __ballot_sync(0xffffffffu, need);
             const bool starving = __any_sync(0xffffffffu, need && !has_path);
-            if (starving || __popc(need_mask) >= REGEN_BATCH) {
+            if (starving || __popc(need_mask) >= a.regen_batch) {
                 if (need) {  // camera sample: event 0, slots 0,1 (mod.rs:814-843)
                     uint32_t rnd[4];
                     philox4x32_10(pixel, (uint32_t)s_next, (uint32_t)(s_next >> 32), 0u, k0, k1, rnd);

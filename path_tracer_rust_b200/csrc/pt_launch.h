@@ -10,7 +10,7 @@ namespace ptb {
 constexpr int TILE_W = 8, TILE_H = 4;  // one warp = one 8x4 pixel tile
 constexpr int RENDER_THREADS = 256;
 constexpr int RENDER_MIN_BLOCKS = 3;
-constexpr int REGEN_BATCH = 12;        // lanes that must be waiting for a camera ray before the ray-gen code runs
+constexpr int REGEN_BATCH = 24;        // lanes that must be waiting for a camera ray before the ray-gen code runs
 
 struct RenderArgs {
     int width, height;
@@ -19,6 +19,7 @@ struct RenderArgs {
     float *sum_rgb;                        // W*H*3 fp32 running sum, reference index order
     int *tile_counter;                     // zeroed before each launch
     int n_tiles, tiles_x;
+    int regen_batch;                       // lanes that must be waiting for a camera ray before the ray-gen code runs
     unsigned long long *segment_counter;   // [0] += closest-hit queries, [1] += BVH nodes fetched, [2] += BVH primitives tested
 };
 

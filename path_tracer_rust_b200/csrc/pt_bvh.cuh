@@ -16,7 +16,7 @@
 // 64-byte accesses, lane c taking child c.
 // A node has two to four children, packed from slot 0; an unused slot carries ref = BVH_EMPTY_REF.
 // ref >= 0: inner node index;  ref < 0: leaf, ~ref = (first_prim << 3) | (count - 1), prims contiguous in bvh_tri.
-// Primitive record = (A | obj), (E1 | tri) in bvh_tri (32 bytes, one 256-bit load) + (E2 | prio) in bvh_sph; a sphere is
+// Primitive record = (A | obj), (E1 | tri) in bvh_tri (32 bytes, one 256-bit load) + (E2 | prio) in bvh_e2; a sphere is
 // stored as (centre | obj), (radius^2, 0, 0 | -1), (0, 0, 0 | prio).
 #pragma once
 #include "pt_device.cuh"
@@ -104,7 +104,7 @@ __device__ __forceinline__ void cswap(float &ta, int &ra, float &tb, int &rb) {
         const int first_ = code_ >> 3, count_ = (code_ & 7) + 1;                                                 \
         for (int k = first_; k < first_ + count_; ++k) {                                                         \
             const F8 ae_ = ld256(sc.bvh_tri + 2 * (size_t)k);                                                    \
-            const float4 A = ae_.a, E1 = ae_.b, E2 = __ldg(&sc.bvh_sph[k]);                                      \
+            const float4 A = ae_.a, E1 = ae_.b, E2 = __ldg(&sc.bvh_e2[k]);                                      \
             const bool is_sphere = __float_as_int(E1.w) < 0;                                                     \
             float tt;                                                                                            \
             if (is_sphere) tt = sphere_t(xyz(A), E1.x, o, d);                                                    \

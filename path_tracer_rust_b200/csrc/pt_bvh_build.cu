@@ -277,7 +277,7 @@ cudaError_t bvh_build(const ptb_scene_desc &desc, const std::vector<char> &in_bv
     out.n_nodes = out.n_tris = out.n_spheres = 0;
     out.max_depth = 0;
     ds.bvh_root = BVH_EMPTY_REF;
-    ds.bvh_nodes = nullptr; ds.bvh_tri = nullptr; ds.bvh_sph = nullptr; ds.n_bvh_nodes = 0;
+    ds.bvh_nodes = nullptr; ds.bvh_tri = nullptr; ds.bvh_e2 = nullptr; ds.n_bvh_nodes = 0;
     if (build_ms) *build_ms = 0.0;
 
     // ---- host: distance bound D, primitive records, pads ----------------------------------------------------------------
@@ -444,7 +444,7 @@ cudaError_t bvh_build(const ptb_scene_desc &desc, const std::vector<char> &in_bv
         if (build_ms) *build_ms = ms;
     }
     out.n_nodes = (unsigned)n_alive; out.n_tris = n_tris; out.n_spheres = n_sph; out.max_depth = h_depth;
-    ds.bvh_nodes = out.nodes; ds.bvh_tri = out.tris; ds.bvh_sph = out.tris + 2 * (size_t)n; ds.n_bvh_nodes = n_alive;
+    ds.bvh_nodes = out.nodes; ds.bvh_tri = out.tris; ds.bvh_e2 = out.tris + 2 * (size_t)n; ds.n_bvh_nodes = n_alive;
 
 done:
     cudaFree(d_recs); cudaFree(d_pads); cudaFree(d_blo); cudaFree(d_bhi); cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_idx);

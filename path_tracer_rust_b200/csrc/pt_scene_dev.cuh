@@ -57,7 +57,7 @@ __device__ __forceinline__ void finish_hit(const DScene &sc, const float4 *__res
     x = o + d * h.t;  // mod.rs:430 / :604
     const int k = h.ref & (REF_SPHERE_BIT - 1);
     if (h.ref & REF_BVH_BIT) {
-        const float4 A = __ldg(&sc.bvh_tri[2 * k]), E1 = __ldg(&sc.bvh_tri[2 * k + 1]), E2 = __ldg(&sc.bvh_sph[k]);
+        const float4 A = __ldg(&sc.bvh_tri[2 * k]), E1 = __ldg(&sc.bvh_tri[2 * k + 1]), E2 = __ldg(&sc.bvh_e2[k]);
         obj = __float_as_int(A.w);
         if (h.ref & REF_SPHERE_BIT) { tri = -1; n = normalize(x - xyz(A)); }
         else { tri = __float_as_int(E1.w); n = normalize(cross(xyz(E1), xyz(E2))); }

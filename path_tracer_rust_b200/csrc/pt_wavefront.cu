@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(WF_THREADS, 4) k_wf_trace_coop(const DScene sc
                 for (int k0 = 0; k0 < count; k0 += 4) {  // leaves hold at most four primitives by construction; stay general
                     const int k = first + k0 + sub;
                     if (k0 + sub < count) {
-                        const float4 A = __ldg(&sc.bvh_tri[2 * (size_t)k]), E1 = __ldg(&sc.bvh_tri[2 * (size_t)k + 1]), E2 = __ldg(&sc.bvh_sph[k]);
+                        const float4 A = __ldg(&sc.bvh_tri[2 * (size_t)k]), E1 = __ldg(&sc.bvh_tri[2 * (size_t)k + 1]), E2 = __ldg(&sc.bvh_e2[k]);
                         const bool is_sphere = __float_as_int(E1.w) < 0;
                         float tt;
                         if (is_sphere) tt = sphere_t(xyz(A), E1.x, o, d);

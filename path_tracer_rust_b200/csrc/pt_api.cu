@@ -343,13 +343,13 @@ extern "C" int ptb_upload_scene(ptb_ctx *ctx, const ptb_scene_desc *desc) {
 
     const double t1 = now_ms();
     double bvh_ms = 0.0;
-    ctx->stats.n_bvh_triangles = ctx->stats.n_bvh_e2eres = ctx->stats.n_bvh_nodes = 0;
+    ctx->stats.n_bvh_triangles = ctx->stats.n_bvh_spheres = ctx->stats.n_bvh_nodes = 0;
     {
         std::string berr;
         cudaError_t e = bvh_build(*desc, in_bvh, prio_base, ctx->bvh_opt, ctx->bvh, ds, ctx->stream, &bvh_ms, berr);
         if (e != cudaSuccess) return cuda_fail(ctx, e, berr.empty() ? "bvh_build" : berr.c_str());
         ctx->stats.n_bvh_triangles = ctx->bvh.n_tris;
-        ctx->stats.n_bvh_e2eres = ctx->bvh.n_spheres;
+        ctx->stats.n_bvh_spheres = ctx->bvh.n_spheres;
         ctx->stats.n_bvh_nodes = ctx->bvh.n_nodes;
     }
     CU(ctx, cudaStreamSynchronize(ctx->stream));

@@ -96,115 +96,113 @@ __global__ void __launch_bounds__(RENDER_THREADS, RENDER_MIN_BLOCKS) k_render(co
     PathStackEntry stk[2];
     V3 Lc[4];                             // finished branches' emission sums; radiance = ((L0+L1)+L2)+L3
 
-    {
-        for (;;) {
-            // a pixel whose samples are all done (no path in flight, no spare ray, budget used up) is written back
-            if (have_pixel && !has_path && !spare_ok && s_next >= s_end) {
-                fb[0] = acc.x; fb[1] = acc.y; fb[2] = acc.z;
-                have_pixel = false;
-            }
-            const unsigned want_mask = __ballot_sync(0xffffffffu, !have_pixel && !retired);
-            if (want_mask) {
-                const int leader = __ffs(want_mask) - 1;
-                unsigned base = 0;
-                if (lane == leader) base = (unsigned)atomicAdd(a.tile_counter, __popc(want_mask));
-                base = __shfl_sync(0xffffffffu, base, leader);
-                if (!have_pixel && !retired) {
-                    const unsigned slot = base + __popc(want_mask & lt_mask);
-                    if (slot >= n_slots) retired = true;
-                    else {
-                        const int tile = (int)(slot >> 5), pos = (int)(slot & 31u);
-                        const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
-                        px = tx * TILE_W + (pos & (TILE_W - 1));
-                        const int row = ty * TILE_H + (pos / TILE_W);
-                        if (px < W && row < H && a.spp_count > 0) {  // (off-image slots of edge tiles are simply skipped)
-                            pixel = (uint32_t)row * (uint32_t)W + (uint32_t)px;
-                            y = H - 1 - row;  // mod.rs:805
-                            fb = a.sum_rgb + 3ull * pixel;
-                            acc = mk3(fb[0], fb[1], fb[2]);
-                            s_next = a.spp_begin;
-                            have_pixel = true;
-                        }
-                    }
-                }
-            }
-            const bool need = have_pixel && !spare_ok && s_next < s_end;
-            const unsigned need_mask = __ballot_sync(0xffffffffu, need);
-            const bool starving = __any_sync(0xffffffffu, need && !has_path);
-            if (starving || __popc(need_mask) >= a.regen_batch) {
-                if (need) {  // camera sample: event 0, slots 0,1 (mod.rs:814-843)
-                    uint32_t rnd[4];
-                    philox4x32_10(pixel, (uint32_t)s_next, (uint32_t)(s_next >> 32), 0u, k0, k1, rnd);
-                    const float ysub = (float)((s_next / 2) % 2), xsub = (float)(s_next % 2);
-                    const float r1 = 2.0f * u32_to_unit(rnd[0]);
-                    const float r2 = 2.0f * u32_to_unit(rnd[1]);
-                    V3 o_unused;
-                    camera_ray(sc, W, H, px, y, xsub, ysub, tent(r1), tent(r2), o_unused, spare_d);
-                    spare_ok = true;
-                    s_next++;
-                }
-            }
-            if (!has_path && spare_ok) {  // start sample s = s_next - 1
-                o = sc.lens_center; d = spare_d;
-                T = mk3(1.f, 1.f, 1.f); L = mk3(0.f, 0.f, 0.f);
-                depth = 0; sp = 0; code = 0; chain_mask = 1u;
-                s = s_next - 1;
-                spare_ok = false;
-                has_path = true;
-            }
-            const unsigned amask = __ballot_sync(0xffffffffu, has_path);
-            if (amask == 0u) {
-                if (__ballot_sync(0xffffffffu, have_pixel || !retired) == 0u) break;  // every lane is out of pixels
-                continue;
-            }
-            if (has_path) {
-                uint32_t rnd[4];
-                // ---- one radiance() call (mod.rs:662): event (code<<4 | new_depth); slots 0 = RR, 1,2 = diffuse, 3 = refraction
-                nseg++;
-                philox4x32_10(pixel, (uint32_t)s, (uint32_t)(s >> 32), ((uint32_t)code << 4) | (uint32_t)(depth + 1), k0, k1, rnd);
-                const Hit h = closest_hit<HAS_BVH>(sc, s_obj, s_tri, o, d, amask);
-                bool cont = false;
-                if (h.ref != REF_NONE) {
-                    int obj, tri;
-                    V3 x, n;
-                    finish_hit(sc, s_obj, s_tri, h, o, d, obj, tri, x, n);
-                    const int new_depth = depth + 1;
-                    ShadeOut so;
-                    shade_hit(sc, obj, n, d, T, new_depth, rnd, so);
-                    if (so.emits) L = L + so.emit;
-                    if (so.cont) {
-                        if (so.split) {  // the reflected child continues this branch, the transmitted one is postponed
-                            const int child = code | (1 << (new_depth - 1));
-                            stk[sp].o = x; stk[sp].d = so.child_d; stk[sp].T = so.child_T; stk[sp].depth = new_depth;
-                            stk[sp].code = child;
-                            chain_mask |= 1u << child;
-                            sp++;
-                        }
-                        o = x; d = so.d; T = so.T;
-                        depth = new_depth;
-                        cont = true;
-                    }
-                }
-                if (!cont) {
-                    if (sp > 0) {  // this branch is finished, continue with a postponed transmitted child
-                        Lc[code] = L;
-                        sp--;
-                        o = stk[sp].o; d = stk[sp].d; T = stk[sp].T; depth = stk[sp].depth; code = stk[sp].code;
-                        L = mk3(0.f, 0.f, 0.f);
-                    } else {  // sample finished: radiance_v += radiance (mod.rs:846)
-                        if (chain_mask != 1u) {
-                            Lc[code] = L;
-                            const V3 z = mk3(0.f, 0.f, 0.f);
-                            L = ((Lc[0] + ((chain_mask & 2u) ? Lc[1] : z)) + ((chain_mask & 4u) ? Lc[2] : z)) + ((chain_mask & 8u) ? Lc[3] : z);
-                        }
-                        acc = acc + L;
-                        has_path = false;
+    for (;;) {
+        // a pixel whose samples are all done (no path in flight, no spare ray, budget used up) is written back
+        if (have_pixel && !has_path && !spare_ok && s_next >= s_end) {
+            fb[0] = acc.x; fb[1] = acc.y; fb[2] = acc.z;
+            have_pixel = false;
+        }
+        const unsigned want_mask = __ballot_sync(0xffffffffu, !have_pixel && !retired);
+        if (want_mask) {
+            const int leader = __ffs(want_mask) - 1;
+            unsigned base = 0;
+            if (lane == leader) base = (unsigned)atomicAdd(a.tile_counter, __popc(want_mask));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (!have_pixel && !retired) {
+                const unsigned slot = base + __popc(want_mask & lt_mask);
+                if (slot >= n_slots) retired = true;
+                else {
+                    const int tile = (int)(slot >> 5), pos = (int)(slot & 31u);
+                    const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
+                    px = tx * TILE_W + (pos & (TILE_W - 1));
+                    const int row = ty * TILE_H + (pos / TILE_W);
+                    if (px < W && row < H && a.spp_count > 0) {  // (off-image slots of edge tiles are simply skipped)
+                        pixel = (uint32_t)row * (uint32_t)W + (uint32_t)px;
+                        y = H - 1 - row;  // mod.rs:805
+                        fb = a.sum_rgb + 3ull * pixel;
+                        acc = mk3(fb[0], fb[1], fb[2]);
+                        s_next = a.spp_begin;
+                        have_pixel = true;
                     }
                 }
             }
         }
-        n_segments += nseg;
+        const bool need = have_pixel && !spare_ok && s_next < s_end;
+        const unsigned need_mask = __ballot_sync(0xffffffffu, need);
+        const bool starving = __any_sync(0xffffffffu, need && !has_path);
+        if (starving || __popc(need_mask) >= a.regen_batch) {
+            if (need) {  // camera sample: event 0, slots 0,1 (mod.rs:814-843)
+                uint32_t rnd[4];
+                philox4x32_10(pixel, (uint32_t)s_next, (uint32_t)(s_next >> 32), 0u, k0, k1, rnd);
+                const float ysub = (float)((s_next / 2) % 2), xsub = (float)(s_next % 2);
+                const float r1 = 2.0f * u32_to_unit(rnd[0]);
+                const float r2 = 2.0f * u32_to_unit(rnd[1]);
+                V3 o_unused;
+                camera_ray(sc, W, H, px, y, xsub, ysub, tent(r1), tent(r2), o_unused, spare_d);
+                spare_ok = true;
+                s_next++;
+            }
+        }
+        if (!has_path && spare_ok) {  // start sample s = s_next - 1
+            o = sc.lens_center; d = spare_d;
+            T = mk3(1.f, 1.f, 1.f); L = mk3(0.f, 0.f, 0.f);
+            depth = 0; sp = 0; code = 0; chain_mask = 1u;
+            s = s_next - 1;
+            spare_ok = false;
+            has_path = true;
+        }
+        const unsigned amask = __ballot_sync(0xffffffffu, has_path);
+        if (amask == 0u) {
+            if (__ballot_sync(0xffffffffu, have_pixel || !retired) == 0u) break;  // every lane is out of pixels
+            continue;
+        }
+        if (has_path) {
+            uint32_t rnd[4];
+            // ---- one radiance() call (mod.rs:662): event (code<<4 | new_depth); slots 0 = RR, 1,2 = diffuse, 3 = refraction
+            nseg++;
+            philox4x32_10(pixel, (uint32_t)s, (uint32_t)(s >> 32), ((uint32_t)code << 4) | (uint32_t)(depth + 1), k0, k1, rnd);
+            const Hit h = closest_hit<HAS_BVH>(sc, s_obj, s_tri, o, d, amask);
+            bool cont = false;
+            if (h.ref != REF_NONE) {
+                int obj, tri;
+                V3 x, n;
+                finish_hit(sc, s_obj, s_tri, h, o, d, obj, tri, x, n);
+                const int new_depth = depth + 1;
+                ShadeOut so;
+                shade_hit(sc, obj, n, d, T, new_depth, rnd, so);
+                if (so.emits) L = L + so.emit;
+                if (so.cont) {
+                    if (so.split) {  // the reflected child continues this branch, the transmitted one is postponed
+                        const int child = code | (1 << (new_depth - 1));
+                        stk[sp].o = x; stk[sp].d = so.child_d; stk[sp].T = so.child_T; stk[sp].depth = new_depth;
+                        stk[sp].code = child;
+                        chain_mask |= 1u << child;
+                        sp++;
+                    }
+                    o = x; d = so.d; T = so.T;
+                    depth = new_depth;
+                    cont = true;
+                }
+            }
+            if (!cont) {
+                if (sp > 0) {  // this branch is finished, continue with a postponed transmitted child
+                    Lc[code] = L;
+                    sp--;
+                    o = stk[sp].o; d = stk[sp].d; T = stk[sp].T; depth = stk[sp].depth; code = stk[sp].code;
+                    L = mk3(0.f, 0.f, 0.f);
+                } else {  // sample finished: radiance_v += radiance (mod.rs:846)
+                    if (chain_mask != 1u) {
+                        Lc[code] = L;
+                        const V3 z = mk3(0.f, 0.f, 0.f);
+                        L = ((Lc[0] + ((chain_mask & 2u) ? Lc[1] : z)) + ((chain_mask & 4u) ? Lc[2] : z)) + ((chain_mask & 8u) ? Lc[3] : z);
+                    }
+                    acc = acc + L;
+                    has_path = false;
+                }
+            }
+        }
     }
+    n_segments += nseg;
     // one atomic per warp
     for (int off = 16; off > 0; off >>= 1) n_segments += __shfl_down_sync(0xffffffffu, n_segments, off);
     if (lane == 0 && n_segments) atomicAdd(a.segment_counter, n_segments);

@@ -68,7 +68,7 @@ struct ptb_ctx {
     std::string err;
     bool has_scene = false;
     DScene ds{};
-    DevBuf<float4> loose_obj, loose_tri, obj_gate, mat_color, mat_emis;
+    DevBuf<float4> loose_obj, loose_tri, loose_pair, obj_gate, mat_color, mat_emis;
     BvhDevice bvh;
     BvhOptions bvh_opt;
     WfWorkspace wf;
@@ -181,7 +181,7 @@ extern "C" const char *ptb_last_error(const ptb_ctx *ctx) { return ctx ? ctx->er
 extern "C" void ptb_destroy(ptb_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    ctx->loose_obj.release(); ctx->loose_tri.release(); ctx->obj_gate.release(); ctx->mat_color.release();
+    ctx->loose_obj.release(); ctx->loose_tri.release(); ctx->loose_pair.release(); ctx->obj_gate.release(); ctx->mat_color.release();
     ctx->mat_emis.release(); ctx->fb.release(); ctx->scratch_f.release(); ctx->scratch_i.release();
     ctx->tile_counter.release(); ctx->seg_counter.release();
     bvh_release(ctx->bvh);
@@ -227,10 +227,10 @@ extern "C" int ptb_create(int device_id, ptb_ctx **out) {
     if ((e = ctx->scratch_f.resize(4)) != cudaSuccess) return bail(e, "cudaMalloc");
     const float a = 1.0f + 1.0f / 8192.0f, c = -(1.0f + 1.0f / 4096.0f);
     if ((e = launch_contraction_probe(a, a, c, ctx->scratch_f.p, ctx->stream)) != cudaSuccess) return bail(e, "probe launch");
-    float probe = 1.0f;
-    if ((e = cudaMemcpyAsync(&probe, ctx->scratch_f.p, 4, cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess) return bail(e, "probe copy");
+    float probe[3] = {1.0f, 1.0f, 1.0f};
+    if ((e = cudaMemcpyAsync(probe, ctx->scratch_f.p, 12, cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess) return bail(e, "probe copy");
     if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return bail(e, "probe sync");
-    if (probe != 0.0f) {
+    if (probe[0] != 0.0f || probe[1] != 0.0f || probe[2] != 0.0f) {
         ptb_destroy(ctx);
         return fail(nullptr, PTB_ERR_STATE, "ptb_create: kernels were built with FMA contraction; rebuild with --fmad=false");
     }
@@ -285,7 +285,8 @@ extern "C" int ptb_upload_scene(ptb_ctx *ctx, const ptb_scene_desc *desc) {
     std::vector<char> in_bvh(nobj, 0);
     choose_bvh_objects(*desc, ctx->max_smem_optin, ctx->bvh_opt, in_bvh);
 
-    std::vector<float4> lobj, ltri;
+    std::vector<float4> lobj, ltri, lpair;
+    uint32_t n_real_loose_tris = 0;
     for (size_t k = nobj; k-- > 0;) {  // reverse index order = the reference's scan order
         const ptb_object &o = desc->objects[k];
         if (in_bvh[k]) continue;
@@ -307,22 +308,37 @@ extern "C" int ptb_upload_scene(ptb_ctx *ctx, const ptb_scene_desc *desc) {
                 ltri.push_back(f4(a.x, a.y, a.z, ibits(static_cast<int32_t>(k))));
                 ltri.push_back(f4(e1.x, e1.y, e1.z, ibits(static_cast<int32_t>(j))));
                 ltri.push_back(f4(e2.x, e2.y, e2.z, ubits(prio_base[k] + static_cast<uint32_t>(j))));
+                n_real_loose_tris++;
+            }
+            if (o.tri_count & 1) {  // pad to a whole pair with a null triangle: det = 0, always rejected (mod.rs:571)
+                ltri.push_back(f4(0, 0, 0, ibits(static_cast<int32_t>(k))));
+                ltri.push_back(f4(0, 0, 0, ibits(-1)));
+                ltri.push_back(f4(0, 0, 0, ubits(0xffffffffu)));
             }
         }
     }
-    const size_t loose_bytes = (lobj.size() + ltri.size()) * sizeof(float4);
+    for (size_t t = 0; t + 1 < ltri.size() / 3; t += 2) {  // pair records for the packed tests (pt_device.cuh: triangle_pair_hit)
+        const float4 *p = &ltri[3 * t], *q = &ltri[3 * (t + 1)];
+        lpair.push_back(f4(p[0].x, q[0].x, p[0].y, q[0].y));
+        lpair.push_back(f4(p[0].z, q[0].z, p[1].x, q[1].x));
+        lpair.push_back(f4(p[1].y, q[1].y, p[1].z, q[1].z));
+        lpair.push_back(f4(p[2].x, q[2].x, p[2].y, q[2].y));
+        lpair.push_back(f4(p[2].z, q[2].z, p[2].w, q[2].w));
+    }
+    const size_t loose_bytes = (lobj.size() + ltri.size() + lpair.size()) * sizeof(float4);
     if (loose_bytes > ctx->max_smem_optin)
         return fail(ctx, PTB_ERR_LIMIT, "ptb_upload_scene: loose primitive list does not fit in shared memory");
 
     CU(ctx, ctx->loose_obj.upload(lobj, ctx->stream));
     CU(ctx, ctx->loose_tri.upload(ltri, ctx->stream));
+    CU(ctx, ctx->loose_pair.upload(lpair, ctx->stream));
     CU(ctx, ctx->obj_gate.upload(gate, ctx->stream));
     CU(ctx, ctx->mat_color.upload(mcol, ctx->stream));
     CU(ctx, ctx->mat_emis.upload(memi, ctx->stream));
 
     DScene &ds = ctx->ds;
     ds = DScene{};
-    ds.loose_obj = ctx->loose_obj.p; ds.loose_tri = ctx->loose_tri.p;
+    ds.loose_obj = ctx->loose_obj.p; ds.loose_tri = ctx->loose_tri.p; ds.loose_pair = ctx->loose_pair.p;
     ds.n_loose_obj = static_cast<int>(lobj.size() / 2); ds.n_loose_tri = static_cast<int>(ltri.size() / 3);
     ds.obj_gate = ctx->obj_gate.p; ds.mat_color = ctx->mat_color.p; ds.mat_emis = ctx->mat_emis.p;
     ds.n_obj = static_cast<int>(nobj);
@@ -356,7 +372,7 @@ extern "C" int ptb_upload_scene(ptb_ctx *ctx, const ptb_scene_desc *desc) {
     ctx->stats.upload_ms = (t1 - t0) + (now_ms() - t1 - bvh_ms > 0 ? now_ms() - t1 - bvh_ms : 0.0);
     ctx->stats.bvh_build_ms = bvh_ms;
     ctx->stats.n_loose_objects = static_cast<uint32_t>(ds.n_loose_obj);
-    ctx->stats.n_loose_triangles = static_cast<uint32_t>(ds.n_loose_tri);
+    ctx->stats.n_loose_triangles = n_real_loose_tris;
     ctx->has_scene = true;
     return PTB_OK;
 }

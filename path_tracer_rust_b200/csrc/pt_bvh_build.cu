@@ -242,10 +242,11 @@ void choose_bvh_objects(const ptb_scene_desc &desc, size_t max_smem_bytes, const
     auto loose_bytes = [&]() {
         size_t b = 0;
         for (size_t k = 0; k < n; ++k)
-            if (!in_bvh[k]) b += 32 + (desc.objects[k].kind == PTB_OBJ_MESH ? 48 * desc.objects[k].tri_count : 0);
+            if (!in_bvh[k]) b += 32 + (desc.objects[k].kind == PTB_OBJ_MESH ? 88 * (desc.objects[k].tri_count + 1) : 0);
         return b;
     };
-    const size_t budget = std::min<size_t>(max_smem_bytes, 96 * 1024);
+    // (a caller that switches the BVH off for testing gets the whole opt-in shared memory of a CTA instead)
+    const size_t budget = opt.min_tris > 1e9 ? max_smem_bytes - 1024 : std::min<size_t>(max_smem_bytes, 96 * 1024);
     while (loose_bytes() > budget) {
         size_t big = n;
         uint64_t big_n = 0;

@@ -265,12 +265,19 @@ __global__ void k_rcp_selftest(unsigned long long *mismatches) {
 }
 
 // a*b+c with operands chosen so that a fused multiply-add gives a different answer
-__global__ void k_contraction_probe(float a, float b, float c, float *out) { out[0] = a * b + c; }
+__global__ void k_contraction_probe(float a, float b, float c, float *out) {
+    out[0] = a * b + c;                                             // scalar multiply then add
+    const float2 p = __fmul2_rn(make_float2(a, a), make_float2(b, b));  // packed multiply (FMUL2) then scalar adds
+    out[1] = p.x + c;
+    out[2] = p.y + c;
+}
 
 // ---------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------
-static size_t loose_smem_bytes(const DScene &sc) { return sizeof(float4) * (2ull * sc.n_loose_obj + 3ull * sc.n_loose_tri); }
+static size_t loose_smem_bytes(const DScene &sc) {
+    return sizeof(float4) * (2ull * sc.n_loose_obj + 3ull * sc.n_loose_tri + 5ull * (sc.n_loose_tri / 2));
+}
 
 cudaError_t launch_rcp_selftest(unsigned long long *d_mismatches, int sm_count, cudaStream_t st) {
     k_rcp_selftest<<<sm_count * 8, 256, 0, st>>>(d_mismatches);

@@ -13,8 +13,10 @@ constexpr int MAX_DEPTH = 12;               // mod.rs:661
 // ---------------------------------------------------------------------------------------------
 // closest hit over the shared-memory ("loose") object list, in the reference's scan order
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void closest_hit_loose(const float4 *__restrict__ s_obj, const float4 *__restrict__ s_tri,
-                                                  int n_obj, V3 o, V3 d, unsigned amask, Hit &best) {
+__device__ __forceinline__ void closest_hit_loose(const DScene &sc, const float4 *__restrict__ s_obj, const float4 *__restrict__ s_tri,
+                                                  V3 o, V3 d, unsigned amask, Hit &best) {
+    const float4 *s_pair = s_tri + 3 * sc.n_loose_tri;
+    const int n_obj = sc.n_loose_obj;
     const float4 *rec = s_obj;
     for (int i = 0; i < n_obj; ++i, rec += 2) {
         const float4 sph = rec[0];
@@ -31,20 +33,15 @@ __device__ __forceinline__ void closest_hit_loose(const float4 *__restrict__ s_o
             // mesh: bounding-sphere gate first (mod.rs:267-277); skip the triangle scan if no lane passes
             const bool pass = sphere_gate(xyz(sph), sph.w, o, d, mb.x);  // for a mesh, mb.x carries r2_inside (never +0)
             if (__any_sync(amask, pass)) {
-                int k = __float_as_int(mb.y);
+                int k = __float_as_int(mb.y);  // even: meshes are padded to whole pairs
                 const int k1 = k + __float_as_int(mb.z);
-                const float4 *tr = s_tri + 3 * k;
-                for (; k + 1 < k1; k += 2, tr += 6) {  // two triangles per trip (wall quads)
+                const float4 *pr = s_pair + 5 * (k >> 1);
+                for (; k < k1; k += 2, pr += 5) {  // two triangles per trip, packed multiplies
                     float ta, tb;
-                    const bool ha = triangle_hit(xyz(tr[0]), xyz(tr[1]), xyz(tr[2]), o, d, ta);
-                    const bool hb = triangle_hit(xyz(tr[3]), xyz(tr[4]), xyz(tr[5]), o, d, tb);
-                    if (pass && ha && ta < best.t) { best.t = ta; best.prio = (uint32_t)__float_as_int(tr[2].w); best.ref = k; }
-                    if (pass && hb && tb < best.t) { best.t = tb; best.prio = (uint32_t)__float_as_int(tr[5].w); best.ref = k + 1; }
-                }
-                if (k < k1) {
-                    float ta;
-                    const bool ha = triangle_hit(xyz(tr[0]), xyz(tr[1]), xyz(tr[2]), o, d, ta);
-                    if (pass && ha && ta < best.t) { best.t = ta; best.prio = (uint32_t)__float_as_int(tr[2].w); best.ref = k; }
+                    bool ha, hb;
+                    triangle_pair_hit(pr, o, d, ha, ta, hb, tb);
+                    if (pass && ha && ta < best.t) { best.t = ta; best.prio = (uint32_t)__float_as_int(pr[4].z); best.ref = k; }
+                    if (pass && hb && tb < best.t) { best.t = tb; best.prio = (uint32_t)__float_as_int(pr[4].w); best.ref = k + 1; }
                 }
             }
         }
@@ -81,15 +78,16 @@ __device__ __forceinline__ Hit closest_hit(const DScene &sc, const float4 *__res
     best.t = __int_as_float(0x7f800000);
     best.prio = PRIO_NONE;
     best.ref = REF_NONE;
-    closest_hit_loose(s_obj, s_tri, sc.n_loose_obj, o, d, amask, best);
+    closest_hit_loose(sc, s_obj, s_tri, o, d, amask, best);
     if (HAS_BVH) bvh_closest_hit(sc, o, d, best);
     return best;
 }
 
 __device__ __forceinline__ void stage_loose(const DScene &sc, float4 *smem, const float4 *&s_obj, const float4 *&s_tri) {
-    const int n0 = 2 * sc.n_loose_obj, n1 = 3 * sc.n_loose_tri;
+    const int n0 = 2 * sc.n_loose_obj, n1 = 3 * sc.n_loose_tri, n2 = 5 * (sc.n_loose_tri / 2);
     for (int i = threadIdx.x; i < n0; i += blockDim.x) smem[i] = __ldg(&sc.loose_obj[i]);
     for (int i = threadIdx.x; i < n1; i += blockDim.x) smem[n0 + i] = __ldg(&sc.loose_tri[i]);
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) smem[n0 + n1 + i] = __ldg(&sc.loose_pair[i]);
     __syncthreads();
     s_obj = smem;
     s_tri = smem + n0;

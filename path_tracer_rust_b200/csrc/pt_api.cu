@@ -68,7 +68,7 @@ struct ptb_ctx {
     std::string err;
     bool has_scene = false;
     DScene ds{};
-    DevBuf<float4> loose_obj, loose_tri, loose_pair, obj_gate, mat_color, mat_emis;
+    DevBuf<float4> loose_obj, loose_tri, obj_gate, mat_color, mat_emis;
     BvhDevice bvh;
     BvhOptions bvh_opt;
     WfWorkspace wf;
@@ -181,7 +181,7 @@ extern "C" const char *ptb_last_error(const ptb_ctx *ctx) { return ctx ? ctx->er
 extern "C" void ptb_destroy(ptb_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    ctx->loose_obj.release(); ctx->loose_tri.release(); ctx->loose_pair.release(); ctx->obj_gate.release(); ctx->mat_color.release();
+    ctx->loose_obj.release(); ctx->loose_tri.release(); ctx->obj_gate.release(); ctx->mat_color.release();
     ctx->mat_emis.release(); ctx->fb.release(); ctx->scratch_f.release(); ctx->scratch_i.release();
     ctx->tile_counter.release(); ctx->seg_counter.release();
     bvh_release(ctx->bvh);
@@ -285,61 +285,70 @@ extern "C" int ptb_upload_scene(ptb_ctx *ctx, const ptb_scene_desc *desc) {
     std::vector<char> in_bvh(nobj, 0);
     choose_bvh_objects(*desc, ctx->max_smem_optin, ctx->bvh_opt, in_bvh);
 
-    std::vector<float4> lobj, ltri, lpair;
-    uint32_t n_real_loose_tris = 0;
+    // the loose object stream and its triangle records (layout: pt_device.cuh, DScene)
+    std::vector<float4> lobj, ltri;
+    uint32_t n_real_loose_tris = 0, n_loose_objects = 0;
     for (size_t k = nobj; k-- > 0;) {  // reverse index order = the reference's scan order
         const ptb_object &o = desc->objects[k];
         if (in_bvh[k]) continue;
+        n_loose_objects++;
         if (o.kind == PTB_OBJ_SPHERE) {
+            const int32_t self = static_cast<int32_t>(lobj.size());
             lobj.push_back(f4(o.position[0], o.position[1], o.position[2], o.radius * o.radius));
-            lobj.push_back(f4(ibits(0), ubits(prio_base[k]), ibits(0), ibits(static_cast<int32_t>(k))));
+            lobj.push_back(f4(ibits(KIND_SPHERE), ubits(prio_base[k]), ibits(self), ibits(static_cast<int32_t>(k))));
         } else {
-            lobj.push_back(gate[k]);
             // gate shortcut (sphere_gate): usable for 0.4 <= r <= 1000, see the derivation there
             const float r2_inside = (o.bs_radius >= 0.4f && o.bs_radius <= 1000.0f) ? (o.bs_radius * o.bs_radius) * 0.999f : -1.0f;
-            lobj.push_back(f4(r2_inside, ibits(static_cast<int32_t>(ltri.size() / 3)), ibits(static_cast<int32_t>(o.tri_count)),
-                              ibits(static_cast<int32_t>(k))));
+            const uint64_t n_padded = (o.tri_count + 1) & ~1ull;
+            const int32_t k_begin = static_cast<int32_t>(ltri.size() / 2);
+            lobj.push_back(gate[k]);
+            lobj.push_back(f4(r2_inside, ibits(k_begin), ibits(static_cast<int32_t>(n_padded)),
+                              ibits(static_cast<int32_t>(2 + 5 * (n_padded / 2)))));
             const V3 off = v3(o.position);
-            for (uint64_t j = 0; j < o.tri_count; ++j) {
-                const ptb_triangle &t = desc->triangles[o.tri_begin + j];
-                // Triangle::transformed then the edge vectors, exactly as per ray in mod.rs:559-561
-                const V3 a = v3(t.a) + off, b = v3(t.b) + off, c = v3(t.c) + off;
-                const V3 e1 = b - a, e2 = c - a;
-                ltri.push_back(f4(a.x, a.y, a.z, ibits(static_cast<int32_t>(k))));
-                ltri.push_back(f4(e1.x, e1.y, e1.z, ibits(static_cast<int32_t>(j))));
-                ltri.push_back(f4(e2.x, e2.y, e2.z, ubits(prio_base[k] + static_cast<uint32_t>(j))));
-                n_real_loose_tris++;
+            // per triangle: A' | E1 | E2 | prio for the pair records, unit normal | ids for the triangle records
+            std::vector<V3> ta(n_padded, mk3(0, 0, 0)), te1(n_padded, mk3(0, 0, 0)), te2(n_padded, mk3(0, 0, 0));
+            std::vector<uint32_t> tp(n_padded, 0xffffffffu);  // (odd count: a null triangle pads the pair, det = 0, always rejected, mod.rs:571)
+            for (uint64_t j = 0; j < n_padded; ++j) {
+                if (j < o.tri_count) {
+                    const ptb_triangle &t = desc->triangles[o.tri_begin + j];
+                    // Triangle::transformed then the edge vectors, exactly as per ray in mod.rs:559-561
+                    const V3 a = v3(t.a) + off, b = v3(t.b) + off, c = v3(t.c) + off;
+                    ta[j] = a; te1[j] = b - a; te2[j] = c - a;
+                    tp[j] = prio_base[k] + static_cast<uint32_t>(j);
+                    n_real_loose_tris++;
+                }
+                const V3 nrm = normalize(cross(te1[j], te2[j]));  // mod.rs:605, the same fp32 operations the reference does per hit
+                ltri.push_back(f4(nrm.x, nrm.y, nrm.z, ibits(static_cast<int32_t>(k))));
+                ltri.push_back(f4(ibits(j < o.tri_count ? static_cast<int32_t>(j) : -1), 0, 0, 0));
             }
-            if (o.tri_count & 1) {  // pad to a whole pair with a null triangle: det = 0, always rejected (mod.rs:571)
-                ltri.push_back(f4(0, 0, 0, ibits(static_cast<int32_t>(k))));
-                ltri.push_back(f4(0, 0, 0, ibits(-1)));
-                ltri.push_back(f4(0, 0, 0, ubits(0xffffffffu)));
+            for (uint64_t j = 0; j < n_padded; j += 2) {  // pair records for the packed tests (pt_device.cuh: triangle_pair_hit)
+                const V3 &a0 = ta[j], &a1 = ta[j + 1], &p0 = te1[j], &p1 = te1[j + 1], &q0 = te2[j], &q1 = te2[j + 1];
+                lobj.push_back(f4(a0.x, a1.x, a0.y, a1.y));
+                lobj.push_back(f4(a0.z, a1.z, p0.x, p1.x));
+                lobj.push_back(f4(p0.y, p1.y, p0.z, p1.z));
+                lobj.push_back(f4(q0.x, q1.x, q0.y, q1.y));
+                lobj.push_back(f4(q0.z, q1.z, ubits(tp[j]), ubits(tp[j + 1])));
             }
         }
     }
-    for (size_t t = 0; t + 1 < ltri.size() / 3; t += 2) {  // pair records for the packed tests (pt_device.cuh: triangle_pair_hit)
-        const float4 *p = &ltri[3 * t], *q = &ltri[3 * (t + 1)];
-        lpair.push_back(f4(p[0].x, q[0].x, p[0].y, q[0].y));
-        lpair.push_back(f4(p[0].z, q[0].z, p[1].x, q[1].x));
-        lpair.push_back(f4(p[1].y, q[1].y, p[1].z, q[1].z));
-        lpair.push_back(f4(p[2].x, q[2].x, p[2].y, q[2].y));
-        lpair.push_back(f4(p[2].z, q[2].z, p[2].w, q[2].w));
-    }
-    const size_t loose_bytes = (lobj.size() + ltri.size() + lpair.size()) * sizeof(float4);
+    lobj.push_back(f4(0, 0, 0, 0));
+    lobj.push_back(f4(ibits(KIND_END), 0, 0, 0));
+    if (lobj.size() >= (1u << 28)) return fail(ctx, PTB_ERR_LIMIT, "ptb_upload_scene: loose primitive list too long");
+    const size_t loose_bytes = (lobj.size() + ltri.size()) * sizeof(float4);
     if (loose_bytes > ctx->max_smem_optin)
         return fail(ctx, PTB_ERR_LIMIT, "ptb_upload_scene: loose primitive list does not fit in shared memory");
 
     CU(ctx, ctx->loose_obj.upload(lobj, ctx->stream));
     CU(ctx, ctx->loose_tri.upload(ltri, ctx->stream));
-    CU(ctx, ctx->loose_pair.upload(lpair, ctx->stream));
     CU(ctx, ctx->obj_gate.upload(gate, ctx->stream));
     CU(ctx, ctx->mat_color.upload(mcol, ctx->stream));
     CU(ctx, ctx->mat_emis.upload(memi, ctx->stream));
 
     DScene &ds = ctx->ds;
     ds = DScene{};
-    ds.loose_obj = ctx->loose_obj.p; ds.loose_tri = ctx->loose_tri.p; ds.loose_pair = ctx->loose_pair.p;
-    ds.n_loose_obj = static_cast<int>(lobj.size() / 2); ds.n_loose_tri = static_cast<int>(ltri.size() / 3);
+    ds.loose_obj = ctx->loose_obj.p; ds.loose_tri = ctx->loose_tri.p;
+    ds.n_loose_f4 = static_cast<int>(lobj.size()); ds.n_loose_obj = static_cast<int>(n_loose_objects);
+    ds.n_loose_tri = static_cast<int>(ltri.size() / 2);
     ds.obj_gate = ctx->obj_gate.p; ds.mat_color = ctx->mat_color.p; ds.mat_emis = ctx->mat_emis.p;
     ds.n_obj = static_cast<int>(nobj);
     ds.bvh_root = BVH_EMPTY_REF;
@@ -429,9 +438,20 @@ extern "C" int ptb_get_stats(const ptb_ctx *ctx, ptb_stats *out) {
 // ------------------------------------------------------------------------------------------------
 // render
 // ------------------------------------------------------------------------------------------------
+static int render_device_impl(ptb_ctx *ctx, int width, int height, uint64_t spp_begin, uint64_t spp_count, uint64_t seed,
+                              float *d_sum_rgb, void *cuda_stream, const volatile int32_t *cancel, volatile uint64_t *samples_done,
+                              bool fresh_frame);
+
 extern "C" int ptb_render_device(ptb_ctx *ctx, int width, int height, uint64_t spp_begin, uint64_t spp_count, uint64_t seed,
                                  float *d_sum_rgb, void *cuda_stream, const volatile int32_t *cancel,
                                  volatile uint64_t *samples_done) {
+    return render_device_impl(ctx, width, height, spp_begin, spp_count, seed, d_sum_rgb, cuda_stream, cancel, samples_done, false);
+}
+
+// fresh_frame: the buffer's content is undefined and counts as zero; the first batch overwrites it instead of accumulating
+static int render_device_impl(ptb_ctx *ctx, int width, int height, uint64_t spp_begin, uint64_t spp_count, uint64_t seed,
+                              float *d_sum_rgb, void *cuda_stream, const volatile int32_t *cancel, volatile uint64_t *samples_done,
+                              bool fresh_frame) {
     if (!ctx) return fail(nullptr, PTB_ERR_ARG, "ptb_render_device: ctx is null");
     if (!ctx->has_scene) return fail(ctx, PTB_ERR_STATE, "ptb_render_device: no scene uploaded");
     if (width <= 0 || height <= 0 || !d_sum_rgb) return fail(ctx, PTB_ERR_ARG, "ptb_render_device: bad argument");
@@ -463,6 +483,7 @@ extern "C" int ptb_render_device(ptb_ctx *ctx, int width, int height, uint64_t s
         const uint64_t n = std::min(batch, spp_count - done);
         a.spp_begin = spp_begin + done;
         a.spp_count = n;
+        a.fb_zero = (fresh_frame && done == 0) ? 1 : 0;
         // auto: the wavefront integrator when the scene has a BVH, and also for images too small to give every resident
         // megakernel warp two pixel tiles (measured: cornell 450x300 974 vs 800 Mpaths/s; at 1920x1080 the megakernel wins)
         const bool small_image = a.n_tiles < 2 * ctx->sm_count * (RENDER_MIN_BLOCKS * RENDER_THREADS / 32);
@@ -480,6 +501,8 @@ extern "C" int ptb_render_device(ptb_ctx *ctx, int width, int height, uint64_t s
             if (samples_done) *samples_done = done * npix;
         }
     }
+    if (fresh_frame && done == 0)  // nothing was rendered (no samples asked for, or cancelled at once): the frame is black
+        CU(ctx, cudaMemsetAsync(d_sum_rgb, 0, npix * 3 * sizeof(float), st));
     CU(ctx, cudaEventRecord(ctx->ev1, st));
     ctx->stats.samples = done * npix;
     if (interactive) {
@@ -519,10 +542,9 @@ extern "C" int ptb_render(ptb_ctx *ctx, int width, int height, uint64_t spp_begi
     CU(ctx, cudaSetDevice(ctx->device));
     const size_t nfl = static_cast<size_t>(width) * static_cast<size_t>(height) * 3;
     CU(ctx, ctx->fb.resize(nfl));
-    CU(ctx, cudaMemsetAsync(ctx->fb.p, 0, nfl * sizeof(float), ctx->stream));
     uint64_t progress = 0;
-    int rc = ptb_render_device(ctx, width, height, spp_begin, spp_count, seed, ctx->fb.p, ctx->stream, cancel,
-                               samples_done ? samples_done : &progress);
+    int rc = render_device_impl(ctx, width, height, spp_begin, spp_count, seed, ctx->fb.p, ctx->stream, cancel,
+                                samples_done ? samples_done : &progress, /*fresh_frame=*/true);
     if (rc < 0) return rc;
     const uint64_t spp_done = ctx->stats.samples / (static_cast<uint64_t>(width) * static_cast<uint64_t>(height));
     if (out_kind == PTB_OUT_MEAN && spp_done > 0)

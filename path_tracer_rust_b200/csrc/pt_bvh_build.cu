@@ -214,12 +214,21 @@ __global__ void k_emit_nodes4(int n_inner, const int *__restrict__ alive, const 
     }
 }
 
+// leaf-order primitive records; out_fin is what shading needs of the winner: (unit normal | obj) for a triangle --
+// normalize(cross(e1, e2)) of mod.rs:605 with the device's un-fused fp32 operations, once per triangle instead of per hit --
+// and (centre | obj) for a sphere
 __global__ void k_gather_prims(const float4 *__restrict__ recs, const int *__restrict__ idx, int n, float4 *__restrict__ out_ae,
-                               float4 *__restrict__ out_e2) {
+                               float4 *__restrict__ out_e2, float4 *__restrict__ out_fin) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int s = idx[i];
-    out_ae[2 * i] = recs[3 * s]; out_ae[2 * i + 1] = recs[3 * s + 1]; out_e2[i] = recs[3 * s + 2];
+    const float4 A = recs[3 * s], E1 = recs[3 * s + 1], E2 = recs[3 * s + 2];
+    out_ae[2 * i] = A; out_ae[2 * i + 1] = E1; out_e2[i] = E2;
+    if (__float_as_int(E1.w) < 0) out_fin[i] = A;
+    else {
+        const V3 nrm = normalize(cross(xyz(E1), xyz(E2)));
+        out_fin[i] = make_float4(nrm.x, nrm.y, nrm.z, A.w);
+    }
 }
 
 template <typename T>
@@ -278,7 +287,7 @@ cudaError_t bvh_build(const ptb_scene_desc &desc, const std::vector<char> &in_bv
     out.n_nodes = out.n_tris = out.n_spheres = 0;
     out.max_depth = 0;
     ds.bvh_root = BVH_EMPTY_REF;
-    ds.bvh_nodes = nullptr; ds.bvh_tri = nullptr; ds.bvh_e2 = nullptr; ds.n_bvh_nodes = 0;
+    ds.bvh_nodes = nullptr; ds.bvh_tri = nullptr; ds.bvh_e2 = nullptr; ds.bvh_fin = nullptr; ds.n_bvh_nodes = 0;
     if (build_ms) *build_ms = 0.0;
 
     // ---- host: distance bound D, primitive records, pads ----------------------------------------------------------------
@@ -380,7 +389,7 @@ cudaError_t bvh_build(const ptb_scene_desc &desc, const std::vector<char> &in_bv
     if (out.cap_tris < (size_t)n) {
         if (out.tris) cudaFree(out.tris);
         out.tris = nullptr; out.cap_tris = 0;
-        BV(dev_alloc(&out.tris, 3 * (size_t)n));
+        BV(dev_alloc(&out.tris, 4 * (size_t)n));
         out.cap_tris = (size_t)n;
     }
 
@@ -435,7 +444,7 @@ cudaError_t bvh_build(const ptb_scene_desc &desc, const std::vector<char> &in_bv
     } else {
         ds.bvh_root = ~((0 << 3) | (n - 1));  // the whole set fits one leaf
     }
-    k_gather_prims<<<B, T, 0, st>>>(d_recs, d_idx2, n, out.tris, out.tris + 2 * (size_t)n);
+    k_gather_prims<<<B, T, 0, st>>>(d_recs, d_idx2, n, out.tris, out.tris + 2 * (size_t)n, out.tris + 3 * (size_t)n);
     BV(cudaGetLastError());
     BV(cudaEventRecord(ev1, st));
     BV(cudaStreamSynchronize(st));
@@ -445,7 +454,8 @@ cudaError_t bvh_build(const ptb_scene_desc &desc, const std::vector<char> &in_bv
         if (build_ms) *build_ms = ms;
     }
     out.n_nodes = (unsigned)n_alive; out.n_tris = n_tris; out.n_spheres = n_sph; out.max_depth = h_depth;
-    ds.bvh_nodes = out.nodes; ds.bvh_tri = out.tris; ds.bvh_e2 = out.tris + 2 * (size_t)n; ds.n_bvh_nodes = n_alive;
+    ds.bvh_nodes = out.nodes; ds.bvh_tri = out.tris; ds.bvh_e2 = out.tris + 2 * (size_t)n; ds.bvh_fin = out.tris + 3 * (size_t)n;
+    ds.n_bvh_nodes = n_alive;
 
 done:
     cudaFree(d_recs); cudaFree(d_pads); cudaFree(d_blo); cudaFree(d_bhi); cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_idx);

@@ -13,7 +13,7 @@ namespace ptb {
 
 struct BvhDevice {
     float4 *nodes = nullptr;  // 8 x float4 per four-wide node
-    float4 *tris = nullptr;   // [2n] (A, E1) pairs then [n] E2, leaf order (triangles and spheres)
+    float4 *tris = nullptr;   // [2n] (A, E1) pairs, [n] E2, [n] shading records, leaf order (triangles and spheres)
     unsigned n_nodes = 0, n_tris = 0, n_spheres = 0;
     int max_depth = 0;
     size_t cap_nodes = 0, cap_tris = 0;

@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(256) k_intersect(const DScene sc, const float 
                 camera_ray(sc, primary_w, primary_h, x, primary_h - 1 - row, 0.f, 0.f, 0.f, 0.f, o, d);
             }
         }
-        const Hit h = closest_hit<HAS_BVH>(sc, s_obj, s_tri, o, d, 0xffffffffu);
+        const Hit h = closest_hit<HAS_BVH>(sc, s_obj, o, d, 0xffffffffu, valid);
         if (valid) {
             int obj = -1, tri = -1;
             V3 x = mk3(0.f, 0.f, 0.f), nn = mk3(0.f, 0.f, 0.f);
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, RENDER_MIN_BLOCKS) k_render(co
                         pixel = (uint32_t)row * (uint32_t)W + (uint32_t)px;
                         y = H - 1 - row;  // mod.rs:805
                         fb = a.sum_rgb + 3ull * pixel;
-                        acc = mk3(fb[0], fb[1], fb[2]);
+                        acc = a.fb_zero ? mk3(0.f, 0.f, 0.f) : mk3(fb[0], fb[1], fb[2]);
                         s_next = a.spp_begin;
                         have_pixel = true;
                     }
@@ -156,12 +156,13 @@ __global__ void __launch_bounds__(RENDER_THREADS, RENDER_MIN_BLOCKS) k_render(co
             if (__ballot_sync(0xffffffffu, have_pixel || !retired) == 0u) break;  // every lane is out of pixels
             continue;
         }
+        // ---- one radiance() call (mod.rs:662): event (code<<4 | new_depth); slots 0 = RR, 1,2 = diffuse, 3 = refraction.
+        // The whole warp walks the object stream (lanes without a path are passengers: full-mask votes, no divergence).
+        uint32_t rnd[4];
+        philox4x32_10(pixel, (uint32_t)s, (uint32_t)(s >> 32), ((uint32_t)code << 4) | (uint32_t)(depth + 1), k0, k1, rnd);
+        const Hit h = closest_hit<HAS_BVH>(sc, s_obj, o, d, 0xffffffffu, has_path);
         if (has_path) {
-            uint32_t rnd[4];
-            // ---- one radiance() call (mod.rs:662): event (code<<4 | new_depth); slots 0 = RR, 1,2 = diffuse, 3 = refraction
             nseg++;
-            philox4x32_10(pixel, (uint32_t)s, (uint32_t)(s >> 32), ((uint32_t)code << 4) | (uint32_t)(depth + 1), k0, k1, rnd);
-            const Hit h = closest_hit<HAS_BVH>(sc, s_obj, s_tri, o, d, amask);
             bool cont = false;
             if (h.ref != REF_NONE) {
                 int obj, tri;
@@ -275,9 +276,6 @@ __global__ void k_contraction_probe(float a, float b, float c, float *out) {
 // ---------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------
-static size_t loose_smem_bytes(const DScene &sc) {
-    return sizeof(float4) * (2ull * sc.n_loose_obj + 3ull * sc.n_loose_tri + 5ull * (sc.n_loose_tri / 2));
-}
 
 cudaError_t launch_rcp_selftest(unsigned long long *d_mismatches, int sm_count, cudaStream_t st) {
     k_rcp_selftest<<<sm_count * 8, 256, 0, st>>>(d_mismatches);

@@ -19,6 +19,7 @@ struct RenderArgs {
     float *sum_rgb;                        // W*H*3 fp32 running sum, reference index order
     int *tile_counter;                     // zeroed before each launch
     int n_tiles, tiles_x;
+    int fb_zero;                           // 1: sum_rgb is to be treated as all zeros (first batch of a fresh frame: no load, no memset)
     int regen_batch;                       // lanes that must be waiting for a camera ray before the ray-gen code runs
     unsigned long long *segment_counter;   // [0] += closest-hit queries, [1] += BVH nodes fetched, [2] += BVH primitives tested
 };

@@ -6,19 +6,17 @@
 
 namespace ptb {
 
-constexpr int KIND_SPHERE = 0;
 constexpr float PI_F = 3.141592653589793f;  // mod.rs:29
 constexpr int MAX_DEPTH = 12;               // mod.rs:661
 
 // ---------------------------------------------------------------------------------------------
-// closest hit over the shared-memory ("loose") object list, in the reference's scan order
+// closest hit over the shared-memory ("loose") object stream, in the reference's scan order.  Every lane named in `vmask` runs
+// this in lock step (broadcast LDS.128).  Lanes that only keep the warp converged ("passengers") pass any finite ray: their
+// result is never read, and they can at worst make the warp scan a mesh that no live lane's gate let through.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void closest_hit_loose(const DScene &sc, const float4 *__restrict__ s_obj, const float4 *__restrict__ s_tri,
-                                                  V3 o, V3 d, unsigned amask, Hit &best) {
-    const float4 *s_pair = s_tri + 3 * sc.n_loose_tri;
-    const int n_obj = sc.n_loose_obj;
+__device__ __forceinline__ void closest_hit_loose(const float4 *__restrict__ s_obj, V3 o, V3 d, unsigned vmask, Hit &best) {
     const float4 *rec = s_obj;
-    for (int i = 0; i < n_obj; ++i, rec += 2) {
+    for (;;) {
         const float4 sph = rec[0];
         const float4 mb = rec[1];
         const int kind = __float_as_int(mb.x);
@@ -27,24 +25,27 @@ __device__ __forceinline__ void closest_hit_loose(const DScene &sc, const float4
             if (t >= 0.0f && t < best.t) {
                 best.t = t;
                 best.prio = (uint32_t)__float_as_int(mb.y);
-                best.ref = REF_SPHERE_BIT | i;
+                best.ref = REF_SPHERE_BIT | __float_as_int(mb.z);
             }
-        } else {
-            // mesh: bounding-sphere gate first (mod.rs:267-277); skip the triangle scan if no lane passes
-            const bool pass = sphere_gate(xyz(sph), sph.w, o, d, mb.x);  // for a mesh, mb.x carries r2_inside (never +0)
-            if (__any_sync(amask, pass)) {
-                int k = __float_as_int(mb.y);  // even: meshes are padded to whole pairs
-                const int k1 = k + __float_as_int(mb.z);
-                const float4 *pr = s_pair + 5 * (k >> 1);
-                for (; k < k1; k += 2, pr += 5) {  // two triangles per trip, packed multiplies
-                    float ta, tb;
-                    bool ha, hb;
-                    triangle_pair_hit(pr, o, d, ha, ta, hb, tb);
-                    if (pass && ha && ta < best.t) { best.t = ta; best.prio = (uint32_t)__float_as_int(pr[4].z); best.ref = k; }
-                    if (pass && hb && tb < best.t) { best.t = tb; best.prio = (uint32_t)__float_as_int(pr[4].w); best.ref = k + 1; }
-                }
+            rec += 2;
+            continue;
+        }
+        if (kind == KIND_END) break;
+        // mesh: bounding-sphere gate first (mod.rs:267-277); skip the triangle scan if no lane passes
+        const bool pass = sphere_gate(xyz(sph), sph.w, o, d, mb.x);
+        if (__any_sync(vmask, pass)) {
+            int k = __float_as_int(mb.y);  // even: meshes are padded to whole pairs
+            const int k1 = k + __float_as_int(mb.z);
+            const float4 *pr = rec + 2;
+            for (; k < k1; k += 2, pr += 5) {  // two triangles per trip, packed multiplies
+                float ta, tb;
+                bool ha, hb;
+                triangle_pair_hit(pr, o, d, ha, ta, hb, tb);
+                if (pass && ha && ta < best.t) { best.t = ta; best.prio = (uint32_t)__float_as_int(pr[4].z); best.ref = k; }
+                if (pass && hb && tb < best.t) { best.t = tb; best.prio = (uint32_t)__float_as_int(pr[4].w); best.ref = k + 1; }
             }
         }
+        rec += __float_as_int(mb.w);
     }
 }
 
@@ -54,43 +55,47 @@ __device__ __forceinline__ void finish_hit(const DScene &sc, const float4 *__res
     x = o + d * h.t;  // mod.rs:430 / :604
     const int k = h.ref & (REF_SPHERE_BIT - 1);
     if (h.ref & REF_BVH_BIT) {
-        const float4 A = __ldg(&sc.bvh_tri[2 * k]), E1 = __ldg(&sc.bvh_tri[2 * k + 1]), E2 = __ldg(&sc.bvh_e2[k]);
-        obj = __float_as_int(A.w);
-        if (h.ref & REF_SPHERE_BIT) { tri = -1; n = normalize(x - xyz(A)); }
-        else { tri = __float_as_int(E1.w); n = normalize(cross(xyz(E1), xyz(E2))); }
+        const float4 F = __ldg(&sc.bvh_fin[k]);
+        obj = __float_as_int(F.w);
+        if (h.ref & REF_SPHERE_BIT) { tri = -1; n = normalize(x - xyz(F)); }
+        else { tri = __float_as_int(__ldg(&sc.bvh_tri[2 * k + 1]).w); n = xyz(F); }
     } else if (h.ref & REF_SPHERE_BIT) {
-        const float4 sph = s_obj[2 * k], mb = s_obj[2 * k + 1];
+        const float4 sph = s_obj[k], mb = s_obj[k + 1];
         obj = __float_as_int(mb.w);
         tri = -1;
         n = normalize(x - xyz(sph));  // mod.rs:431
     } else {
-        const float4 A = s_tri[3 * k], E1 = s_tri[3 * k + 1], E2 = s_tri[3 * k + 2];
-        obj = __float_as_int(A.w);
-        tri = __float_as_int(E1.w);
-        n = normalize(cross(xyz(E1), xyz(E2)));  // mod.rs:605
+        const float4 N = s_tri[2 * k];
+        obj = __float_as_int(N.w);
+        tri = __float_as_int(s_tri[2 * k + 1].x);
+        n = xyz(N);  // normalize(cross(e1, e2)) of mod.rs:605, evaluated once per triangle on the host with the same operations
     }
 }
 
+// `live` lanes get their closest hit; all lanes of `vmask` must call (the loose scan votes)
 template <bool HAS_BVH>
-__device__ __forceinline__ Hit closest_hit(const DScene &sc, const float4 *__restrict__ s_obj, const float4 *__restrict__ s_tri,
-                                           V3 o, V3 d, unsigned amask) {
+__device__ __forceinline__ Hit closest_hit(const DScene &sc, const float4 *__restrict__ s_obj, V3 o, V3 d, unsigned vmask, bool live) {
     Hit best;
     best.t = __int_as_float(0x7f800000);
     best.prio = PRIO_NONE;
     best.ref = REF_NONE;
-    closest_hit_loose(sc, s_obj, s_tri, o, d, amask, best);
-    if (HAS_BVH) bvh_closest_hit(sc, o, d, best);
+    closest_hit_loose(s_obj, o, d, vmask, best);
+    if (HAS_BVH) {
+        if (live) bvh_closest_hit(sc, o, d, best);
+    }
     return best;
 }
 
 __device__ __forceinline__ void stage_loose(const DScene &sc, float4 *smem, const float4 *&s_obj, const float4 *&s_tri) {
-    const int n0 = 2 * sc.n_loose_obj, n1 = 3 * sc.n_loose_tri, n2 = 5 * (sc.n_loose_tri / 2);
+    const int n0 = sc.n_loose_f4, n1 = 2 * sc.n_loose_tri;
     for (int i = threadIdx.x; i < n0; i += blockDim.x) smem[i] = __ldg(&sc.loose_obj[i]);
     for (int i = threadIdx.x; i < n1; i += blockDim.x) smem[n0 + i] = __ldg(&sc.loose_tri[i]);
-    for (int i = threadIdx.x; i < n2; i += blockDim.x) smem[n0 + n1 + i] = __ldg(&sc.loose_pair[i]);
     __syncthreads();
     s_obj = smem;
     s_tri = smem + n0;
+}
+__host__ __device__ __forceinline__ size_t loose_smem_bytes(const DScene &sc) {
+    return sizeof(float4) * ((size_t)sc.n_loose_f4 + 2ull * (size_t)sc.n_loose_tri);
 }
 
 

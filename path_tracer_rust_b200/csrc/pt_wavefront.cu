@@ -26,11 +26,11 @@ constexpr int WF_THREADS = 256;
 constexpr int WF_CHUNK = 512;  // rays a warp takes from the queue per global atomic
 constexpr int WF_SSTACK = 12;  // traversal-stack entries per lane kept in shared memory (deeper entries go to local memory)
 
-__device__ __forceinline__ void store_loose_hit(const WfQueue &q, size_t j, const float4 *s_obj, const float4 *s_tri, const DScene &sc,
-                                                V3 o, V3 d, unsigned amask) {
+// (called by the lanes of `amask` only: they are all live)
+__device__ __forceinline__ void store_loose_hit(const WfQueue &q, size_t j, const float4 *s_obj, V3 o, V3 d, unsigned amask) {
     Hit best;
     best.t = __int_as_float(0x7f800000); best.prio = PRIO_NONE; best.ref = REF_NONE;
-    closest_hit_loose(sc, s_obj, s_tri, o, d, amask, best);
+    closest_hit_loose(s_obj, o, d, amask, best);
     q.hit_t[j] = best.t; q.hit_ref[j] = best.ref; q.hit_prio[j] = best.prio;
 }
 
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(256) k_wf_generate(const DScene sc, int W, int
         q.d[p] = make_float4(d.x, d.y, d.z, __int_as_float(0));
         q.T[p] = make_float4(1.f, 1.f, 1.f, 0.f);
         q.L[p] = make_float4(0.f, 0.f, 0.f, 0.f);
-        store_loose_hit(q, p, s_obj, s_tri, sc, o, d, amask);
+        store_loose_hit(q, p, s_obj, o, d, amask);
     }
 }
 
@@ -388,12 +388,12 @@ __global__ void __launch_bounds__(256) k_wf_shade(const DScene sc, const WfQueue
             if (n_out >= 1) {
                 const int j = base + __popc(m1 & lt_mask);
                 nq.o[j] = c_o; nq.d[j] = c_d; nq.T[j] = c_T; nq.L[j] = c_L;
-                store_loose_hit(nq, j, s_obj, s_tri, sc, mk3(c_o.x, c_o.y, c_o.z), mk3(c_d.x, c_d.y, c_d.z), m1);
+                store_loose_hit(nq, j, s_obj, mk3(c_o.x, c_o.y, c_o.z), mk3(c_d.x, c_d.y, c_d.z), m1);
             }
             if (n_out == 2) {
                 const int j = base + __popc(m1) + __popc(m2 & lt_mask);
                 nq.o[j] = k_o; nq.d[j] = k_d; nq.T[j] = k_T; nq.L[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                store_loose_hit(nq, j, s_obj, s_tri, sc, mk3(k_o.x, k_o.y, k_o.z), mk3(k_d.x, k_d.y, k_d.z), m2);
+                store_loose_hit(nq, j, s_obj, mk3(k_o.x, k_o.y, k_o.z), mk3(k_d.x, k_d.y, k_d.z), m2);
             }
         }
     }
@@ -401,11 +401,11 @@ __global__ void __launch_bounds__(256) k_wf_shade(const DScene sc, const WfQueue
 
 // radiance_v += radiance(sample) for the K samples of the batch, in sample order (mod.rs:846)
 __global__ void __launch_bounds__(256) k_wf_accumulate(const float4 *__restrict__ slots, unsigned long long n_paths, unsigned npix,
-                                                       unsigned K, float *__restrict__ sum_rgb) {
+                                                       unsigned K, float *__restrict__ sum_rgb, const int fb_zero) {
     const unsigned stride = gridDim.x * blockDim.x;
     for (unsigned pixel = blockIdx.x * blockDim.x + threadIdx.x; pixel < npix; pixel += stride) {
         float *fb = sum_rgb + 3ull * pixel;
-        V3 acc = mk3(fb[0], fb[1], fb[2]);
+        V3 acc = fb_zero ? mk3(0.f, 0.f, 0.f) : mk3(fb[0], fb[1], fb[2]);
         for (unsigned k = 0; k < K; ++k) {
             const size_t p = (size_t)k * npix + pixel;
             const float4 a = slots[p], b = slots[n_paths + p], c = slots[2 * n_paths + p], e = slots[3 * n_paths + p];
@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(256) k_wf_accumulate(const float4 *__restrict_
     }
 }
 
-size_t loose_smem(const DScene &sc) { return sizeof(float4) * (2ull * sc.n_loose_obj + 3ull * sc.n_loose_tri + 5ull * (sc.n_loose_tri / 2)); }
+size_t loose_smem(const DScene &sc) { return loose_smem_bytes(sc); }
 
 }  // namespace
 
@@ -511,7 +511,7 @@ cudaError_t wavefront_render(const DScene &sc, const RenderArgs &a, WfWorkspace 
                                                        n_paths, npix, s0, a.seed, a.segment_counter);
             *launches += 2;
         }
-        k_wf_accumulate<<<wide_blocks, 256, 0, st>>>(w.slots, n_paths, npix, k_now, a.sum_rgb);
+        k_wf_accumulate<<<wide_blocks, 256, 0, st>>>(w.slots, n_paths, npix, k_now, a.sum_rgb, (a.fb_zero && done == 0) ? 1 : 0);
         (*launches)++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         done += k_now;

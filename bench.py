@@ -168,6 +168,8 @@ def main():
     ap.add_argument("--workload", default="cornell4k", choices=sorted(WORKLOADS))
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (development only; recorded in config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
+                    help="backend option (ptb_set_option), development only; recorded in config")
     ap.add_argument("--reduce", default="peer", choices=["peer", "nccl"],
                     help="N>1: sum the ranks' framebuffers with the fused peer-memory kernel (default) or with an NCCL reduce")
     args = ap.parse_args()
@@ -202,6 +204,9 @@ def main():
     scene_path, scene_base = resolve_scene(scene_id, rank)
     scene = P.Scene.load(scene_path, base_dir=scene_base)
     be = P.Backend(local_rank)
+    for kv in args.opt:
+        name, _, value = kv.partition("=")
+        be.set_option(name, float(value))
     be.upload_scene(scene)
     use_peer = world > 1 and args.reduce == "peer"
     frame = None
@@ -352,9 +357,10 @@ def main():
             "ms_per_step": total_ms / max(args.steps, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: scenes/{scene_id}.json {W}x{H} x {spp} spp, spp sharded over {world} GPU(s), "
-                                   + ("fused peer-memory reduce+resolve kernel over NVLink (CUDA IPC)" if use_peer else "NCCL fp32 sum-reduce"), "scene": scene_id, "width": W, "height": H, "spp": spp,
+                                   + ("fused peer-memory reduce+resolve kernel over NVLink (CUDA IPC)" if use_peer
+                                      else ("NCCL fp32 sum-reduce" if world > 1 else "no reduce step")), "scene": scene_id, "width": W, "height": H, "spp": spp,
                        "spp_reduced_for_development": reduced, "l2": "flushed between steps (256 MiB device write)",
-                       "parallelism": f"spp-shard x{world}"},
+                       "parallelism": f"spp-shard x{world}", "backend_options": list(args.opt)},
             "mray_segments_per_s": seg_rate, "segments_per_sample": seg_total / (samples_per_step * args.steps),
             "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": scene_bytes, "d2h_bytes_per_step": nfl * 4,
                     "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps},

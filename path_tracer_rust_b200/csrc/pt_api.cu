@@ -75,6 +75,9 @@ struct ptb_ctx {
     int integrator = 0;             // 0 = auto (wavefront when the scene has a BVH), 1 = megakernel, 2 = wavefront
     double wavefront_paths = 8388608.0;  // ray segments in flight per wavefront batch
     int regen_batch = REGEN_BATCH;
+    // wf_sort: trace the rays of bounce >= 1 in (direction octant, Morton cell) order [1] or (cell, octant) order [2].  Off by
+    // default: measured slower on B200 (the sort, the read-back and the scattered ray fetch cost more than the traversal gains)
+    int wf_sort = 0;
     int wf_refill = 8, wf_descend_min = 12, wf_coop = 0;  // wf_coop: experimental four-lanes-per-ray trace kernel (slower)
     DevBuf<float> fb, scratch_f;
     DevBuf<int> scratch_i;
@@ -408,6 +411,7 @@ extern "C" int ptb_set_option(ptb_ctx *ctx, const char *key, double value) {
     else if (k == "wf_refill") ctx->wf_refill = (int)value;
     else if (k == "wf_descend_min") ctx->wf_descend_min = (int)value;
     else if (k == "wf_coop") ctx->wf_coop = (int)value;
+    else if (k == "wf_sort") ctx->wf_sort = (int)value;
     else if (k == "regen_batch") ctx->regen_batch = std::max(1, std::min(32, (int)value));
     else if (k == "integrator") ctx->integrator = (int)value;
     else if (k == "wavefront_paths") ctx->wavefront_paths = std::max(1024.0, value);
@@ -489,7 +493,7 @@ static int render_device_impl(ptb_ctx *ctx, int width, int height, uint64_t spp_
         const bool small_image = a.n_tiles < 2 * ctx->sm_count * (RENDER_MIN_BLOCKS * RENDER_THREADS / 32);
         const bool wavefront = ctx->integrator == 2 || (ctx->integrator == 0 && (ctx->ds.bvh_root != BVH_EMPTY_REF || small_image));
         if (wavefront) {
-            CU(ctx, wavefront_render(ctx->ds, a, ctx->wf, ctx->sm_count, (size_t)ctx->wavefront_paths, ctx->wf_refill, ctx->wf_descend_min, ctx->wf_coop, st, &ctx->stats.kernel_launches));
+            CU(ctx, wavefront_render(ctx->ds, a, ctx->wf, ctx->sm_count, (size_t)ctx->wavefront_paths, ctx->wf_refill, ctx->wf_descend_min, ctx->wf_coop, ctx->wf_sort, st, &ctx->stats.kernel_launches));
         } else {
             CU(ctx, cudaMemsetAsync(ctx->tile_counter.p, 0, sizeof(int), st));
             CU(ctx, launch_render(ctx->ds, a, ctx->sm_count, st));

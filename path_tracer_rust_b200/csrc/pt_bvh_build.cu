@@ -456,6 +456,11 @@ cudaError_t bvh_build(const ptb_scene_desc &desc, const std::vector<char> &in_bv
     out.n_nodes = (unsigned)n_alive; out.n_tris = n_tris; out.n_spheres = n_sph; out.max_depth = h_depth;
     ds.bvh_nodes = out.nodes; ds.bvh_tri = out.tris; ds.bvh_e2 = out.tris + 2 * (size_t)n; ds.bvh_fin = out.tris + 3 * (size_t)n;
     ds.n_bvh_nodes = n_alive;
+    ds.world_lo = mk3((float)lo[0], (float)lo[1], (float)lo[2]);
+    {
+        auto inv = [&](int k) { const double e = hi[k] - lo[k]; return (float)(e > 0 ? 1.0 / e : 0.0); };
+        ds.world_inv = mk3(inv(0), inv(1), inv(2));
+    }
 
 done:
     cudaFree(d_recs); cudaFree(d_pads); cudaFree(d_blo); cudaFree(d_bhi); cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_idx);

@@ -30,11 +30,16 @@ struct WfWorkspace {
     int2 *overflow = nullptr; // cooperative trace kernel: stack entries beyond the shared-memory part, per sub-warp
     size_t cap_overflow = 0;
     size_t cap_paths = 0;
+    // ray reordering between bounces (wf_sort): keys / queue indices, double-buffered for the radix sort, and its scratch
+    unsigned *sort_keys[2] = {nullptr, nullptr};
+    int *sort_idx[2] = {nullptr, nullptr};
+    void *sort_tmp = nullptr;
+    size_t sort_tmp_bytes = 0, cap_sort = 0;
 };
 
 void wf_release(WfWorkspace &w);
 cudaError_t wavefront_render(const DScene &sc, const RenderArgs &a, WfWorkspace &w, int sm_count, size_t target_paths, int refill,
-                             int descend_min, int coop, cudaStream_t st,
+                             int descend_min, int coop, int sort_mode, cudaStream_t st,
                              unsigned *launches);
 
 }  // namespace ptb

@@ -88,7 +88,9 @@ def test_random_scene_matches_oracle(tmp_path, idx, n_spheres, n_inline, n_file_
     ref_fb, ref_st = osc.render_sum(W, H, spp, seed=idx)
     for opts in ({"integrator": 1}, {"integrator": 2, "wavefront_paths": 5000},
                  {"integrator": 1, "bvh_min_tris": 1e18, "bvh_min_spheres": 1e18}, {"integrator": 2, "bvh_min_tris": 2, "bvh_min_spheres": 2},
-                 {"integrator": 2, "wf_coop": 1, "bvh_leaf_max": 4, "bvh_min_tris": 2, "bvh_min_spheres": 2}):
+                 {"integrator": 2, "wf_coop": 1, "bvh_leaf_max": 4, "bvh_min_tris": 2, "bvh_min_spheres": 2},
+                 {"integrator": 2, "wf_sort": 1, "bvh_min_tris": 2, "bvh_min_spheres": 2},
+                 {"integrator": 2, "wf_sort": 2, "wavefront_paths": 5000, "bvh_min_tris": 2, "bvh_min_spheres": 2}):
         be = P.Backend(0)
         try:
             for k, v in opts.items():

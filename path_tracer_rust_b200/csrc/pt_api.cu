@@ -468,6 +468,7 @@ static int render_device_impl(ptb_ctx *ctx, int width, int height, uint64_t spp_
 
     RenderArgs a{};
     a.width = width; a.height = height; a.seed = seed; a.sum_rgb = d_sum_rgb;
+    philox_round_keys(seed, a.rk);
     a.tile_counter = ctx->tile_counter.p; a.segment_counter = ctx->seg_counter.p;
     a.regen_batch = ctx->regen_batch;
     a.tiles_x = (width + TILE_W - 1) / TILE_W;

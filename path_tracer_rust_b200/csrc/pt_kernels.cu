@@ -68,7 +68,6 @@ __global__ void __launch_bounds__(RENDER_THREADS, RENDER_MIN_BLOCKS) k_render(co
 
     const int lane = threadIdx.x & 31;
     const int W = a.width, H = a.height;
-    const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
     unsigned long long n_segments = 0;
 
     // Work distribution: pixels are enumerated tile-major (slot = tile * 32 + position inside the 8x4 tile) and handed out
@@ -133,7 +132,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, RENDER_MIN_BLOCKS) k_render(co
         if (starving || __popc(need_mask) >= a.regen_batch) {
             if (need) {  // camera sample: event 0, slots 0,1 (mod.rs:814-843)
                 uint32_t rnd[4];
-                philox4x32_10(pixel, (uint32_t)s_next, (uint32_t)(s_next >> 32), 0u, k0, k1, rnd);
+                philox4x32_10(pixel, (uint32_t)s_next, (uint32_t)(s_next >> 32), 0u, a.rk, rnd);
                 const float ysub = (float)((s_next / 2) % 2), xsub = (float)(s_next % 2);
                 const float r1 = 2.0f * u32_to_unit(rnd[0]);
                 const float r2 = 2.0f * u32_to_unit(rnd[1]);
@@ -159,7 +158,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, RENDER_MIN_BLOCKS) k_render(co
         // ---- one radiance() call (mod.rs:662): event (code<<4 | new_depth); slots 0 = RR, 1,2 = diffuse, 3 = refraction.
         // The whole warp walks the object stream (lanes without a path are passengers: full-mask votes, no divergence).
         uint32_t rnd[4];
-        philox4x32_10(pixel, (uint32_t)s, (uint32_t)(s >> 32), ((uint32_t)code << 4) | (uint32_t)(depth + 1), k0, k1, rnd);
+        philox4x32_10(pixel, (uint32_t)s, (uint32_t)(s >> 32), ((uint32_t)code << 4) | (uint32_t)(depth + 1), a.rk, rnd);
         const Hit h = closest_hit<HAS_BVH>(sc, s_obj, o, d, 0xffffffffu, has_path);
         if (has_path) {
             nseg++;

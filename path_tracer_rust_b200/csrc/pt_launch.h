@@ -16,6 +16,7 @@ struct RenderArgs {
     int width, height;
     unsigned long long spp_begin, spp_count;
     unsigned long long seed;
+    PhiloxKeys rk;                         // round keys of `seed` (philox_round_keys)
     float *sum_rgb;                        // W*H*3 fp32 running sum, reference index order
     int *tile_counter;                     // zeroed before each launch
     int n_tiles, tiles_x;

@@ -146,14 +146,15 @@ __device__ __forceinline__ void shade_hit(const DScene &sc, int obj, V3 n, V3 d_
                 out.d = rd; out.T = Tc;
             } else {  // Refract, mod.rs:729-788
                 const bool into = dot(n, nl) > 0.0f;
-                const float nnt = into ? PTB_DIV(1.0f, 1.5f) : PTB_DIV(1.5f, 1.0f);
+                constexpr float NNT_IN = 1.0f / 1.5f, NNT_OUT = 1.5f / 1.0f;  // IEEE divisions folded by the compiler (mod.rs:733)
+                const float nnt = into ? NNT_IN : NNT_OUT;
                 const float ddn = dot(d_in, nl);
                 const float cos2t = 1.0f - nnt * nnt * (1.0f - ddn * ddn);
                 if (cos2t < 0.0f) {  // total internal reflection
                     out.d = rd; out.T = Tc;
                 } else {
                     const V3 tdir = normalize(d_in * nnt - n * ((into ? 1.0f : -1.0f) * (ddn * nnt + PTB_SQRT(cos2t))));
-                    const float r0 = PTB_DIV(0.5f * 0.5f, 2.5f * 2.5f);
+                    constexpr float r0 = (0.5f * 0.5f) / (2.5f * 2.5f);  // (1.5-1)^2 / (1.5+1)^2, folded (mod.rs:751-753)
                     const float c = 1.0f - (into ? -ddn : dot(tdir, n));
                     const float c2 = c * c;
                     const float re = r0 + (1.0f - r0) * (c * (c2 * c2));

@@ -75,6 +75,7 @@ struct ptb_ctx {
     int integrator = 0;             // 0 = auto (wavefront when the scene has a BVH), 1 = megakernel, 2 = wavefront
     double wavefront_paths = 8388608.0;  // ray segments in flight per wavefront batch
     int regen_batch = REGEN_BATCH;
+    double quad_min_ratio = 0.125;  // one-pair meshes with gate radius >= this x scene diagonal are tested without the warp vote
     // wf_sort: trace the rays of bounce >= 1 in (direction octant, Morton cell) order [1] or (cell, octant) order [2].  Off by
     // default: measured slower on B200 (the sort, the read-back and the scattered ray fetch cost more than the traversal gains)
     int wf_sort = 0;
@@ -288,6 +289,27 @@ extern "C" int ptb_upload_scene(ptb_ctx *ctx, const ptb_scene_desc *desc) {
     std::vector<char> in_bvh(nobj, 0);
     choose_bvh_objects(*desc, ctx->max_smem_optin, ctx->bvh_opt, in_bvh);
 
+    double scene_diag = 0.0;  // diagonal of the box around every primitive
+    {
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        auto grow = [&](double x, double y, double z, double r) {
+            const double p[3] = {x, y, z};
+            for (int c = 0; c < 3; ++c) { lo[c] = std::min(lo[c], p[c] - r); hi[c] = std::max(hi[c], p[c] + r); }
+        };
+        for (size_t k = 0; k < nobj; ++k) {
+            const ptb_object &o = desc->objects[k];
+            if (o.kind == PTB_OBJ_SPHERE) grow(o.position[0], o.position[1], o.position[2], o.radius);
+            else
+                for (uint64_t j = 0; j < o.tri_count; ++j) {
+                    const ptb_triangle &t = desc->triangles[o.tri_begin + j];
+                    grow(t.a[0] + o.position[0], t.a[1] + o.position[1], t.a[2] + o.position[2], 0);
+                    grow(t.b[0] + o.position[0], t.b[1] + o.position[1], t.b[2] + o.position[2], 0);
+                    grow(t.c[0] + o.position[0], t.c[1] + o.position[1], t.c[2] + o.position[2], 0);
+                }
+        }
+        if (hi[0] >= lo[0]) scene_diag = std::sqrt((hi[0] - lo[0]) * (hi[0] - lo[0]) + (hi[1] - lo[1]) * (hi[1] - lo[1]) + (hi[2] - lo[2]) * (hi[2] - lo[2]));
+    }
+
     // the loose object stream and its triangle records (layout: pt_device.cuh, DScene)
     std::vector<float4> lobj, ltri;
     uint32_t n_real_loose_tris = 0, n_loose_objects = 0;
@@ -305,7 +327,9 @@ extern "C" int ptb_upload_scene(ptb_ctx *ctx, const ptb_scene_desc *desc) {
             const uint64_t n_padded = (o.tri_count + 1) & ~1ull;
             const int32_t k_begin = static_cast<int32_t>(ltri.size() / 2);
             lobj.push_back(gate[k]);
-            lobj.push_back(f4(r2_inside, ibits(k_begin), ibits(static_cast<int32_t>(n_padded)),
+            // a one-pair mesh whose gate sphere is large against the scene skips the per-mesh warp vote (closest_hit_loose)
+            const bool always = n_padded == 2 && static_cast<double>(o.bs_radius) >= ctx->quad_min_ratio * scene_diag;
+            lobj.push_back(f4(r2_inside, ibits(k_begin), ibits(always ? 0 : static_cast<int32_t>(n_padded)),
                               ibits(static_cast<int32_t>(2 + 5 * (n_padded / 2)))));
             const V3 off = v3(o.position);
             // per triangle: A' | E1 | E2 | prio for the pair records, unit normal | ids for the triangle records
@@ -412,6 +436,7 @@ extern "C" int ptb_set_option(ptb_ctx *ctx, const char *key, double value) {
     else if (k == "wf_descend_min") ctx->wf_descend_min = (int)value;
     else if (k == "wf_coop") ctx->wf_coop = (int)value;
     else if (k == "wf_sort") ctx->wf_sort = (int)value;
+    else if (k == "quad_min_ratio") ctx->quad_min_ratio = value;
     else if (k == "regen_batch") ctx->regen_batch = std::max(1, std::min(32, (int)value));
     else if (k == "integrator") ctx->integrator = (int)value;
     else if (k == "wavefront_paths") ctx->wavefront_paths = std::max(1024.0, value);

@@ -31,11 +31,25 @@ __device__ __forceinline__ void closest_hit_loose(const float4 *__restrict__ s_o
             continue;
         }
         if (kind == KIND_END) break;
-        // mesh: bounding-sphere gate first (mod.rs:267-277); skip the triangle scan if no lane passes
+        // mesh: bounding-sphere gate first (mod.rs:267-277)
         const bool pass = sphere_gate(xyz(sph), sph.w, o, d, mb.x);
-        if (__any_sync(vmask, pass)) {
+        const int n_tri = __float_as_int(mb.z);
+        if (n_tri == 0) {
+            // one pair (a wall quad) whose gate sphere is large against the scene, marked by the host: some lane nearly always
+            // passes, so the pair is tested without asking the warp first -- no vote, no loop; `pass` still decides acceptance
+            const int k = __float_as_int(mb.y);
+            const float4 *pr = rec + 2;
+            float ta, tb;
+            bool ha, hb;
+            triangle_pair_hit(pr, o, d, ha, ta, hb, tb);
+            if (pass && ha && ta < best.t) { best.t = ta; best.prio = (uint32_t)__float_as_int(pr[4].z); best.ref = k; }
+            if (pass && hb && tb < best.t) { best.t = tb; best.prio = (uint32_t)__float_as_int(pr[4].w); best.ref = k + 1; }
+            rec += 7;
+            continue;
+        }
+        if (__any_sync(vmask, pass)) {  // skip the triangle scan if no lane passes
             int k = __float_as_int(mb.y);  // even: meshes are padded to whole pairs
-            const int k1 = k + __float_as_int(mb.z);
+            const int k1 = k + n_tri;
             const float4 *pr = rec + 2;
             for (; k < k1; k += 2, pr += 5) {  // two triangles per trip, packed multiplies
                 float ta, tb;
@@ -129,6 +143,12 @@ __device__ __forceinline__ void shade_hit(const DScene &sc, int obj, V3 n, V3 d_
     out.d = d_in; out.T = T_in; out.child_d = d_in; out.child_T = T_in;
     if (alive) {
         const V3 Tc = T_in * color;
+        // The diffuse arm and the refraction arm both end in a normalize(); the lanes of both run it together (`pre`, `norm`),
+        // so the few glass lanes of a warp do not make it issue a second copy.  Every lane still performs exactly the
+        // operations of its own arm, in the reference's order.
+        V3 pre = d_in, rd = d_in;
+        bool norm = false, refr = false, into = false;
+        float ddn = 0.0f;
         if (refl == 0) {  // Diffuse, mod.rs:687-715
             const float r1 = 2.0f * PI_F * u32_to_unit(rnd[1]);
             const float r2 = u32_to_unit(rnd[2]);
@@ -138,36 +158,44 @@ __device__ __forceinline__ void shade_hit(const DScene &sc, int obj, V3 n, V3 d_
             const V3 v = cross(w, u);
             float sn, cs;
             sincos_det(r1, sn, cs);
-            out.d = normalize(u * cs * r2s + v * sn * r2s + w * PTB_SQRT(1.0f - r2));
+            pre = u * cs * r2s + v * sn * r2s + w * PTB_SQRT(1.0f - r2);
+            norm = true;
             out.T = Tc;
         } else {
-            const V3 rd = d_in - n * 2.0f * dot(n, d_in);  // mod.rs:722-723
-            if (refl == 1) {  // Specular
-                out.d = rd; out.T = Tc;
-            } else {  // Refract, mod.rs:729-788
-                const bool into = dot(n, nl) > 0.0f;
-                constexpr float NNT_IN = 1.0f / 1.5f, NNT_OUT = 1.5f / 1.0f;  // IEEE divisions folded by the compiler (mod.rs:733)
+            rd = d_in - n * 2.0f * dot(n, d_in);  // mod.rs:722-723
+            out.d = rd; out.T = Tc;               // Specular; also refraction's total internal reflection (mod.rs:743-744)
+            if (refl == 2) {                      // Refract, mod.rs:729-788
+                into = dot(n, nl) > 0.0f;
+                constexpr float NNT_IN = 1.0f / 1.5f, NNT_OUT = 1.5f / 1.0f;  // IEEE divisions folded by the compiler (mod.rs:739)
                 const float nnt = into ? NNT_IN : NNT_OUT;
-                const float ddn = dot(d_in, nl);
+                ddn = dot(d_in, nl);
                 const float cos2t = 1.0f - nnt * nnt * (1.0f - ddn * ddn);
-                if (cos2t < 0.0f) {  // total internal reflection
-                    out.d = rd; out.T = Tc;
-                } else {
-                    const V3 tdir = normalize(d_in * nnt - n * ((into ? 1.0f : -1.0f) * (ddn * nnt + PTB_SQRT(cos2t))));
-                    constexpr float r0 = (0.5f * 0.5f) / (2.5f * 2.5f);  // (1.5-1)^2 / (1.5+1)^2, folded (mod.rs:751-753)
-                    const float c = 1.0f - (into ? -ddn : dot(tdir, n));
-                    const float c2 = c * c;
-                    const float re = r0 + (1.0f - r0) * (c * (c2 * c2));
-                    const float tr = 1.0f - re;
-                    const float p = 0.25f + 0.5f * re;
-                    if (new_depth > 2) {
-                        if (u32_to_unit(rnd[3]) < p) { out.T = Tc * PTB_DIV(re, p); out.d = rd; }
-                        else { out.T = Tc * PTB_DIV(tr, 1.0f - p); out.d = tdir; }
-                    } else {  // deterministic two-way split (mod.rs:776-785)
-                        out.split = true;
-                        out.child_d = tdir; out.child_T = Tc * tr;
-                        out.T = Tc * re; out.d = rd;
-                    }
+                if (!(cos2t < 0.0f)) {
+                    pre = d_in * nnt - n * ((into ? 1.0f : -1.0f) * (ddn * nnt + PTB_SQRT(cos2t)));
+                    norm = true; refr = true;
+                }
+            }
+        }
+        if (norm) {
+            const V3 nd = normalize(pre);
+            if (!refr) out.d = nd;
+            else {
+                const V3 tdir = nd;
+                constexpr float r0 = (0.5f * 0.5f) / (2.5f * 2.5f);  // (nt-nc)^2 / (nt+nc)^2, folded (mod.rs:750-752)
+                const float c = 1.0f - (into ? -ddn : dot(tdir, n));
+                const float c2 = c * c;
+                const float re = r0 + (1.0f - r0) * (c * (c2 * c2));
+                const float tr = 1.0f - re;
+                const float p = 0.25f + 0.5f * re;
+                if (new_depth > 2) {  // Russian roulette between the two children: one division for whichever is taken
+                    const bool reflect = u32_to_unit(rnd[3]) < p;
+                    const float num = reflect ? re : tr, den = reflect ? p : 1.0f - p;
+                    out.T = Tc * PTB_DIV(num, den);
+                    out.d = reflect ? rd : tdir;
+                } else {  // deterministic two-way split (mod.rs:776-785)
+                    out.split = true;
+                    out.child_d = tdir; out.child_T = Tc * tr;
+                    out.T = Tc * re; out.d = rd;
                 }
             }
         }

@@ -89,6 +89,8 @@ def test_random_scene_matches_oracle(tmp_path, idx, n_spheres, n_inline, n_file_
     for opts in ({"integrator": 1}, {"integrator": 2, "wavefront_paths": 5000},
                  {"integrator": 1, "bvh_min_tris": 1e18, "bvh_min_spheres": 1e18}, {"integrator": 2, "bvh_min_tris": 2, "bvh_min_spheres": 2},
                  {"integrator": 2, "wf_coop": 1, "bvh_leaf_max": 4, "bvh_min_tris": 2, "bvh_min_spheres": 2},
+                 {"integrator": 1, "quad_min_ratio": 0.0},      # every one-pair mesh takes the vote-free path, failing gates included
+                 {"integrator": 2, "quad_min_ratio": 1e9},      # none does
                  {"integrator": 2, "wf_sort": 1, "bvh_min_tris": 2, "bvh_min_spheres": 2},
                  {"integrator": 2, "wf_sort": 2, "wavefront_paths": 5000, "bvh_min_tris": 2, "bvh_min_spheres": 2}):
         be = P.Backend(0)

@@ -113,13 +113,22 @@ const char *ptb_last_error(const ptb_ctx *ctx); /* ctx may be NULL: last error o
  * triangles A'=a+pos, E1, E2 with the reference's own roundings), uploads, builds the device BVH. */
 int ptb_upload_scene(ptb_ctx *ctx, const ptb_scene_desc *desc);
 int ptb_get_stats(const ptb_ctx *ctx, ptb_stats *out);
+/* Diagnostic, host only (no GPU, no context): the shared-memory scene stream (float4 records, layout in DESIGN.md section 3) and the
+ * per-triangle shading records exactly as ptb_upload_scene builds them when every object stays in the lock-step list.  Call with
+ * NULL buffers to get the sizes.  Used by the CPU tests to check the flattening against the oracle without a GPU. */
+int ptb_flatten_loose(const ptb_scene_desc *desc, double quad_min_ratio, float *stream, uint64_t stream_cap_floats,
+                      uint64_t *stream_floats, float *tris, uint64_t tris_cap_floats, uint64_t *tris_floats);
 /* Tuning knobs, effective from the next ptb_upload_scene (results never depend on them, only speed):
  *   "bvh_min_tris"    meshes with at least this many triangles are traversed through the BVH (default 24; a huge value = brute force)
  *   "bvh_min_spheres" scenes with at least this many spheres put them in the BVH (default 48)
  *   "integrator"      0 = auto (wavefront when the scene has a BVH, else megakernel), 1 = megakernel, 2 = wavefront
  *   "wavefront_paths" ray segments in flight per wavefront batch (default 2^23)
  *   "bvh_leaf_max" (1..8, default 2), "wf_refill", "wf_descend_min", "wf_coop" (experimental four-lanes-per-ray trace kernel,
- *   default 0): traversal tuning, see DESIGN.md */
+ *   default 0), "wf_sort" (trace bounce >= 1 in octant/Morton-cell order: 0 off = default, 1, 2; measured slower): traversal
+ *   tuning, see DESIGN.md
+ *   "quad_min_ratio"  a two-triangle mesh whose bounding-sphere radius is at least this fraction of the scene diagonal is tested
+ *                     without the per-mesh warp vote (default 0.125; 0 = every two-triangle mesh, a huge value = none)
+ *   "regen_batch"     lanes that must be waiting for a camera ray before the ray-generation code runs (default 24) */
 int ptb_set_option(ptb_ctx *ctx, const char *key, double value);
 /* Device self-test: the kernels' own correctly-rounded reciprocal (MUFU.RCP + 2 FFMA, no range check) is compared with
  * __frcp_rn over every float whose exponent field is in [1, 252]; *mismatches must come back 0. */

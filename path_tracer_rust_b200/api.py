@@ -71,7 +71,7 @@ ABI_SYMBOLS = ["ptb_scene_load_json", "ptb_scene_load_json_ex", "ptb_scene_save_
                "ptb_render", "ptb_render_device", "ptb_resolve_device", "ptb_primary_hits", "ptb_intersect",
                "ptb_to_int_with_gamma_correction", "ptb_write_ppm", "ptb_hash_pixels", "ptb_device_alloc", "ptb_device_free",
                "ptb_device_memset", "ptb_device_to_host", "ptb_device_sync", "ptb_ipc_export", "ptb_ipc_open", "ptb_ipc_close",
-               "ptb_peer_reduce_resolve"]
+               "ptb_peer_reduce_resolve", "ptb_flatten_loose"]
 
 
 def load_library():
@@ -101,6 +101,8 @@ def load_library():
         L.ptb_last_error.argtypes = [C.c_void_p]
         L.ptb_upload_scene.argtypes = [C.c_void_p, C.POINTER(_SceneDesc)]
         L.ptb_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        L.ptb_flatten_loose.argtypes = [C.POINTER(_SceneDesc), C.c_double, fp, C.c_uint64, C.POINTER(C.c_uint64), fp, C.c_uint64,
+                                        C.POINTER(C.c_uint64)]
         L.ptb_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
         L.ptb_selftest.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         L.ptb_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, fp,
@@ -231,6 +233,21 @@ class Scene:
     def objects(self):
         d = self._desc.contents
         return [d.objects[i] for i in range(d.n_objects)]
+
+    def flatten_loose(self, quad_min_ratio: float = 0.125):
+        """Diagnostic, host only: (object stream [n, 4], triangle records [m, 4]) as fp32 arrays, exactly what ptb_upload_scene
+        stages into shared memory when every object stays in the lock-step list (layout: DESIGN.md section 3).  Needs no GPU."""
+        L = load_library()
+        ns, nt = C.c_uint64(), C.c_uint64()
+        rc = L.ptb_flatten_loose(self._desc, quad_min_ratio, None, 0, C.byref(ns), None, 0, C.byref(nt))
+        if rc != PTB_OK:
+            raise BackendError(rc, L.ptb_last_error(None).decode())
+        stream = np.zeros(max(ns.value, 1), np.float32)
+        tris = np.zeros(max(nt.value, 1), np.float32)
+        rc = L.ptb_flatten_loose(self._desc, quad_min_ratio, _fp(stream), ns.value, C.byref(ns), _fp(tris), nt.value, C.byref(nt))
+        if rc != PTB_OK:
+            raise BackendError(rc, L.ptb_last_error(None).decode())
+        return stream[:ns.value].reshape(-1, 4), tris[:nt.value].reshape(-1, 4)
 
     def __del__(self):
         if getattr(self, "_h", None):

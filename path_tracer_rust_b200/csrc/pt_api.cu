@@ -243,80 +243,77 @@ extern "C" int ptb_create(int device_id, ptb_ctx **out) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// scene flatten + upload
+// scene flatten (pure host code) + upload
 // ------------------------------------------------------------------------------------------------
-extern "C" int ptb_upload_scene(ptb_ctx *ctx, const ptb_scene_desc *desc) {
-    if (!ctx || !desc) return fail(ctx, PTB_ERR_ARG, "ptb_upload_scene: null argument");
-    if (desc->n_objects && !desc->objects) return fail(ctx, PTB_ERR_ARG, "ptb_upload_scene: objects is null");
-    if (desc->n_objects > (1u << 28) || desc->n_triangles > (1u << 28))
-        return fail(ctx, PTB_ERR_LIMIT, "ptb_upload_scene: more than 2^28 objects or triangles");
-    CU(ctx, cudaSetDevice(ctx->device));
-    const double t0 = now_ms();
-    const size_t nobj = desc->n_objects;
-    for (size_t i = 0; i < nobj; ++i) {
+namespace {
+
+const char *validate_desc(const ptb_scene_desc *desc, int &code) {  // nullptr = fine
+    code = PTB_ERR_ARG;
+    if (desc->n_objects && !desc->objects) return "objects is null";
+    if (desc->n_objects > (1u << 28) || desc->n_triangles > (1u << 28)) { code = PTB_ERR_LIMIT; return "more than 2^28 objects or triangles"; }
+    if (desc->n_triangles && !desc->triangles) return "triangles is null";
+    for (size_t i = 0; i < desc->n_objects; ++i) {
         const ptb_object &o = desc->objects[i];
-        if (o.kind != PTB_OBJ_SPHERE && o.kind != PTB_OBJ_MESH) return fail(ctx, PTB_ERR_ARG, "ptb_upload_scene: bad object kind");
-        if (o.reflect_type < 0 || o.reflect_type > 2) return fail(ctx, PTB_ERR_ARG, "ptb_upload_scene: bad reflect_type");
+        if (o.kind != PTB_OBJ_SPHERE && o.kind != PTB_OBJ_MESH) return "bad object kind";
+        if (o.reflect_type < 0 || o.reflect_type > 2) return "bad reflect_type";
         if (o.kind == PTB_OBJ_MESH && (o.tri_begin > desc->n_triangles || o.tri_count > desc->n_triangles - o.tri_begin))
-            return fail(ctx, PTB_ERR_ARG, "ptb_upload_scene: triangle range out of bounds");
+            return "triangle range out of bounds";
     }
+    return nullptr;
+}
 
-    // prio = rank in the reference's scan order: objects last-to-first (mod.rs:637), triangles first-to-last (mod.rs:558)
-    std::vector<uint32_t> prio_base(nobj, 0);
-    {
-        uint64_t run = 0;
-        for (size_t k = nobj; k-- > 0;) {
-            prio_base[k] = static_cast<uint32_t>(run);
-            run += desc->objects[k].kind == PTB_OBJ_SPHERE ? 1 : desc->objects[k].tri_count;
-        }
-        if (run >= 0xffffffffull) return fail(ctx, PTB_ERR_LIMIT, "ptb_upload_scene: too many primitives");
+// prio = rank in the reference's scan order: objects last-to-first (mod.rs:637), triangles first-to-last (mod.rs:558)
+bool scan_priorities(const ptb_scene_desc &desc, std::vector<uint32_t> &prio_base) {
+    prio_base.assign(desc.n_objects, 0);
+    uint64_t run = 0;
+    for (size_t k = desc.n_objects; k-- > 0;) {
+        prio_base[k] = static_cast<uint32_t>(run);
+        run += desc.objects[k].kind == PTB_OBJ_SPHERE ? 1 : desc.objects[k].tri_count;
     }
+    return run < 0xffffffffull;
+}
 
-    std::vector<float4> gate(nobj), mcol(nobj), memi(nobj);
-    for (size_t i = 0; i < nobj; ++i) {
-        const ptb_object &o = desc->objects[i];
-        gate[i] = f4(0, 0, 0, 0);
-        if (o.kind == PTB_OBJ_MESH) {
-            const V3 c = v3(o.bs_position) + v3(o.position);  // mod.rs:268
-            gate[i] = f4(c.x, c.y, c.z, o.bs_radius * o.bs_radius);  // radius.powi(2), mod.rs:416
-        }
-        mcol[i] = f4(o.color[0], o.color[1], o.color[2], ibits(o.reflect_type));
-        const bool emits = o.emission[0] != 0.0f || o.emission[1] != 0.0f || o.emission[2] != 0.0f;
-        memi[i] = f4(o.emission[0], o.emission[1], o.emission[2], ibits(emits ? 1 : 0));
+float4 gate_sphere(const ptb_object &o) {
+    if (o.kind != PTB_OBJ_MESH) return f4(0, 0, 0, 0);
+    const V3 c = v3(o.bs_position) + v3(o.position);           // mod.rs:268
+    return f4(c.x, c.y, c.z, o.bs_radius * o.bs_radius);        // radius.powi(2), mod.rs:416
+}
+
+double scene_diagonal(const ptb_scene_desc &desc) {  // diagonal of the box around every primitive
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    auto grow = [&](double x, double y, double z, double r) {
+        const double p[3] = {x, y, z};
+        for (int c = 0; c < 3; ++c) { lo[c] = std::min(lo[c], p[c] - r); hi[c] = std::max(hi[c], p[c] + r); }
+    };
+    for (size_t k = 0; k < desc.n_objects; ++k) {
+        const ptb_object &o = desc.objects[k];
+        if (o.kind == PTB_OBJ_SPHERE) grow(o.position[0], o.position[1], o.position[2], o.radius);
+        else
+            for (uint64_t j = 0; j < o.tri_count; ++j) {
+                const ptb_triangle &t = desc.triangles[o.tri_begin + j];
+                grow(t.a[0] + o.position[0], t.a[1] + o.position[1], t.a[2] + o.position[2], 0);
+                grow(t.b[0] + o.position[0], t.b[1] + o.position[1], t.b[2] + o.position[2], 0);
+                grow(t.c[0] + o.position[0], t.c[1] + o.position[1], t.c[2] + o.position[2], 0);
+            }
     }
+    if (hi[0] < lo[0]) return 0.0;
+    return std::sqrt((hi[0] - lo[0]) * (hi[0] - lo[0]) + (hi[1] - lo[1]) * (hi[1] - lo[1]) + (hi[2] - lo[2]) * (hi[2] - lo[2]));
+}
 
-    // split: which objects go to the BVH, which stay in the lock-step shared-memory list
-    std::vector<char> in_bvh(nobj, 0);
-    choose_bvh_objects(*desc, ctx->max_smem_optin, ctx->bvh_opt, in_bvh);
+struct LooseFlat {
+    std::vector<float4> obj, tri;  // the object stream and the triangle records (layout: pt_device.cuh, DScene)
+    uint32_t n_objects = 0, n_real_tris = 0;
+};
 
-    double scene_diag = 0.0;  // diagonal of the box around every primitive
-    {
-        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-        auto grow = [&](double x, double y, double z, double r) {
-            const double p[3] = {x, y, z};
-            for (int c = 0; c < 3; ++c) { lo[c] = std::min(lo[c], p[c] - r); hi[c] = std::max(hi[c], p[c] + r); }
-        };
-        for (size_t k = 0; k < nobj; ++k) {
-            const ptb_object &o = desc->objects[k];
-            if (o.kind == PTB_OBJ_SPHERE) grow(o.position[0], o.position[1], o.position[2], o.radius);
-            else
-                for (uint64_t j = 0; j < o.tri_count; ++j) {
-                    const ptb_triangle &t = desc->triangles[o.tri_begin + j];
-                    grow(t.a[0] + o.position[0], t.a[1] + o.position[1], t.a[2] + o.position[2], 0);
-                    grow(t.b[0] + o.position[0], t.b[1] + o.position[1], t.b[2] + o.position[2], 0);
-                    grow(t.c[0] + o.position[0], t.c[1] + o.position[1], t.c[2] + o.position[2], 0);
-                }
-        }
-        if (hi[0] >= lo[0]) scene_diag = std::sqrt((hi[0] - lo[0]) * (hi[0] - lo[0]) + (hi[1] - lo[1]) * (hi[1] - lo[1]) + (hi[2] - lo[2]) * (hi[2] - lo[2]));
-    }
-
-    // the loose object stream and its triangle records (layout: pt_device.cuh, DScene)
-    std::vector<float4> lobj, ltri;
-    uint32_t n_real_loose_tris = 0, n_loose_objects = 0;
-    for (size_t k = nobj; k-- > 0;) {  // reverse index order = the reference's scan order
-        const ptb_object &o = desc->objects[k];
+// the objects with in_bvh[k] == 0, in the reference's scan order
+void flatten_loose(const ptb_scene_desc &desc, const std::vector<char> &in_bvh, const std::vector<uint32_t> &prio_base,
+                   double quad_min_ratio, LooseFlat &out) {
+    const double scene_diag = scene_diagonal(desc);
+    std::vector<float4> &lobj = out.obj, &ltri = out.tri;
+    for (size_t k = desc.n_objects; k-- > 0;) {  // reverse index order = the reference's scan order
+        const ptb_object &o = desc.objects[k];
         if (in_bvh[k]) continue;
-        n_loose_objects++;
+        out.n_objects++;
         if (o.kind == PTB_OBJ_SPHERE) {
             const int32_t self = static_cast<int32_t>(lobj.size());
             lobj.push_back(f4(o.position[0], o.position[1], o.position[2], o.radius * o.radius));
@@ -326,9 +323,9 @@ extern "C" int ptb_upload_scene(ptb_ctx *ctx, const ptb_scene_desc *desc) {
             const float r2_inside = (o.bs_radius >= 0.4f && o.bs_radius <= 1000.0f) ? (o.bs_radius * o.bs_radius) * 0.999f : -1.0f;
             const uint64_t n_padded = (o.tri_count + 1) & ~1ull;
             const int32_t k_begin = static_cast<int32_t>(ltri.size() / 2);
-            lobj.push_back(gate[k]);
+            lobj.push_back(gate_sphere(o));
             // a one-pair mesh whose gate sphere is large against the scene skips the per-mesh warp vote (closest_hit_loose)
-            const bool always = n_padded == 2 && static_cast<double>(o.bs_radius) >= ctx->quad_min_ratio * scene_diag;
+            const bool always = n_padded == 2 && static_cast<double>(o.bs_radius) >= quad_min_ratio * scene_diag;
             lobj.push_back(f4(r2_inside, ibits(k_begin), ibits(always ? 0 : static_cast<int32_t>(n_padded)),
                               ibits(static_cast<int32_t>(2 + 5 * (n_padded / 2)))));
             const V3 off = v3(o.position);
@@ -337,12 +334,12 @@ extern "C" int ptb_upload_scene(ptb_ctx *ctx, const ptb_scene_desc *desc) {
             std::vector<uint32_t> tp(n_padded, 0xffffffffu);  // (odd count: a null triangle pads the pair, det = 0, always rejected, mod.rs:571)
             for (uint64_t j = 0; j < n_padded; ++j) {
                 if (j < o.tri_count) {
-                    const ptb_triangle &t = desc->triangles[o.tri_begin + j];
+                    const ptb_triangle &t = desc.triangles[o.tri_begin + j];
                     // Triangle::transformed then the edge vectors, exactly as per ray in mod.rs:559-561
                     const V3 a = v3(t.a) + off, b = v3(t.b) + off, c = v3(t.c) + off;
                     ta[j] = a; te1[j] = b - a; te2[j] = c - a;
                     tp[j] = prio_base[k] + static_cast<uint32_t>(j);
-                    n_real_loose_tris++;
+                    out.n_real_tris++;
                 }
                 const V3 nrm = normalize(cross(te1[j], te2[j]));  // mod.rs:605, the same fp32 operations the reference does per hit
                 ltri.push_back(f4(nrm.x, nrm.y, nrm.z, ibits(static_cast<int32_t>(k))));
@@ -360,6 +357,56 @@ extern "C" int ptb_upload_scene(ptb_ctx *ctx, const ptb_scene_desc *desc) {
     }
     lobj.push_back(f4(0, 0, 0, 0));
     lobj.push_back(f4(ibits(KIND_END), 0, 0, 0));
+}
+
+}  // namespace
+
+// Diagnostic, host only (no GPU, no context): the shared-memory scene stream and triangle records exactly as ptb_upload_scene
+// builds them when every object stays in the lock-step list.  Lets the layout be checked on a machine without a GPU.
+extern "C" int ptb_flatten_loose(const ptb_scene_desc *desc, double quad_min_ratio, float *stream, uint64_t stream_cap_floats,
+                                 uint64_t *stream_floats, float *tris, uint64_t tris_cap_floats, uint64_t *tris_floats) {
+    if (!desc || !stream_floats || !tris_floats) return fail(nullptr, PTB_ERR_ARG, "ptb_flatten_loose: null argument");
+    int code = PTB_OK;
+    if (const char *why = validate_desc(desc, code)) return fail(nullptr, code, std::string("ptb_flatten_loose: ") + why);
+    std::vector<uint32_t> prio_base;
+    if (!scan_priorities(*desc, prio_base)) return fail(nullptr, PTB_ERR_LIMIT, "ptb_flatten_loose: too many primitives");
+    LooseFlat flat;
+    flatten_loose(*desc, std::vector<char>(desc->n_objects, 0), prio_base, quad_min_ratio, flat);
+    *stream_floats = 4 * flat.obj.size();
+    *tris_floats = 4 * flat.tri.size();
+    if (stream && stream_cap_floats >= *stream_floats && !flat.obj.empty()) std::memcpy(stream, flat.obj.data(), *stream_floats * sizeof(float));
+    if (tris && tris_cap_floats >= *tris_floats && !flat.tri.empty()) std::memcpy(tris, flat.tri.data(), *tris_floats * sizeof(float));
+    return PTB_OK;
+}
+
+extern "C" int ptb_upload_scene(ptb_ctx *ctx, const ptb_scene_desc *desc) {
+    if (!ctx || !desc) return fail(ctx, PTB_ERR_ARG, "ptb_upload_scene: null argument");
+    int code = PTB_OK;
+    if (const char *why = validate_desc(desc, code)) return fail(ctx, code, std::string("ptb_upload_scene: ") + why);
+    CU(ctx, cudaSetDevice(ctx->device));
+    const double t0 = now_ms();
+    const size_t nobj = desc->n_objects;
+
+    std::vector<uint32_t> prio_base;
+    if (!scan_priorities(*desc, prio_base)) return fail(ctx, PTB_ERR_LIMIT, "ptb_upload_scene: too many primitives");
+
+    std::vector<float4> gate(nobj), mcol(nobj), memi(nobj);
+    for (size_t i = 0; i < nobj; ++i) {
+        const ptb_object &o = desc->objects[i];
+        gate[i] = gate_sphere(o);
+        mcol[i] = f4(o.color[0], o.color[1], o.color[2], ibits(o.reflect_type));
+        const bool emits = o.emission[0] != 0.0f || o.emission[1] != 0.0f || o.emission[2] != 0.0f;
+        memi[i] = f4(o.emission[0], o.emission[1], o.emission[2], ibits(emits ? 1 : 0));
+    }
+
+    // split: which objects go to the BVH, which stay in the lock-step shared-memory list
+    std::vector<char> in_bvh(nobj, 0);
+    choose_bvh_objects(*desc, ctx->max_smem_optin, ctx->bvh_opt, in_bvh);
+
+    LooseFlat flat;
+    flatten_loose(*desc, in_bvh, prio_base, ctx->quad_min_ratio, flat);
+    const std::vector<float4> &lobj = flat.obj, &ltri = flat.tri;
+    const uint32_t n_real_loose_tris = flat.n_real_tris, n_loose_objects = flat.n_objects;
     if (lobj.size() >= (1u << 28)) return fail(ctx, PTB_ERR_LIMIT, "ptb_upload_scene: loose primitive list too long");
     const size_t loose_bytes = (lobj.size() + ltri.size()) * sizeof(float4);
     if (loose_bytes > ctx->max_smem_optin)

@@ -1,5 +1,11 @@
-import sys, os
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+#!/usr/bin/env python
+"""Worst-case rays for the BVH padding (needs a GPU): 2 M rays grazing mctri.off triangles at |det| ~ 1e-4, closest hits of a BVH
+built with 0 %, 1 %, 10 % and 100 % of the analytic padding against the brute-force scan.  python tools/pad_check.py"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import numpy as np, ctypes as C
 import path_tracer_rust_b200 as P
 f32=np.float32

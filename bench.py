@@ -36,7 +36,7 @@ WORKLOADS = {
     "mesh_1080p": ("mesh", 1920, 1080, 1024),        # configs[2]
     "synthetic4k": ("synthetic", 3840, 2160, 1024),  # configs[4]: 1.31 M-triangle displaced icosphere + 10 k spheres
 }
-SYNTHETIC = dict(level=8, n_spheres=10000, scale=4.0)
+SYNTHETIC = dict(level=8, n_spheres=10000, scale=10.0)   # S = 10 as BASELINE.md C5 / SURVEY.md 8d state
 
 
 def resolve_scene(scene_id: str, rank: int = 0):

@@ -313,6 +313,10 @@ void flatten_loose(const ptb_scene_desc &desc, const std::vector<char> &in_bvh, 
     for (size_t k = desc.n_objects; k-- > 0;) {  // reverse index order = the reference's scan order
         const ptb_object &o = desc.objects[k];
         if (in_bvh[k]) continue;
+        // A mesh without triangles can never be hit (mod.rs:558 loops zero times).  It must not enter the stream: a triangle
+        // count of 0 in a mesh header is the marker of a vote-free wall quad (closest_hit_loose), which would then read the
+        // following records as a pair and lose its place in the stream.
+        if (o.kind == PTB_OBJ_MESH && o.tri_count == 0) continue;
         out.n_objects++;
         if (o.kind == PTB_OBJ_SPHERE) {
             const int32_t self = static_cast<int32_t>(lobj.size());

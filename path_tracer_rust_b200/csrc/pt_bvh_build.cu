@@ -251,7 +251,8 @@ void choose_bvh_objects(const ptb_scene_desc &desc, size_t max_smem_bytes, const
     auto loose_bytes = [&]() {
         size_t b = 0;
         for (size_t k = 0; k < n; ++k)
-            if (!in_bvh[k]) b += 32 + (desc.objects[k].kind == PTB_OBJ_MESH ? 88 * (desc.objects[k].tri_count + 1) : 0);
+            if (!in_bvh[k] && !(desc.objects[k].kind == PTB_OBJ_MESH && desc.objects[k].tri_count == 0))  // (empty meshes are dropped)
+                b += 32 + (desc.objects[k].kind == PTB_OBJ_MESH ? 88 * (desc.objects[k].tri_count + 1) : 0);
         return b;
     };
     // (a caller that switches the BVH off for testing gets the whole opt-in shared memory of a CTA instead)

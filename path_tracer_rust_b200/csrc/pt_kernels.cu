@@ -40,7 +40,10 @@ __global__ void __launch_bounds__(256) k_intersect(const DScene sc, const float 
                 camera_ray(sc, primary_w, primary_h, x, primary_h - 1 - row, 0.f, 0.f, 0.f, 0.f, o, d);
             }
         }
-        const Hit h = closest_hit<HAS_BVH>(sc, s_obj, o, d, 0xffffffffu, valid);
+        // caller rays need not be normalised (the reference's intersect_scene takes any direction): the gate shortcut that
+        // assumes |d| = 1 is switched off for the lanes whose direction is not unit length to 1e-3
+        const bool unit_dir = fabsf(dot(d, d) - 1.0f) <= 1e-3f;
+        const Hit h = closest_hit<HAS_BVH>(sc, s_obj, o, d, 0xffffffffu, valid, unit_dir);
         if (valid) {
             int obj = -1, tri = -1;
             V3 x = mk3(0.f, 0.f, 0.f), nn = mk3(0.f, 0.f, 0.f);

@@ -14,7 +14,10 @@ constexpr int MAX_DEPTH = 12;               // mod.rs:661
 // this in lock step (broadcast LDS.128).  Lanes that only keep the warp converged ("passengers") pass any finite ray: their
 // result is never read, and they can at worst make the warp scan a mesh that no live lane's gate let through.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void closest_hit_loose(const float4 *__restrict__ s_obj, V3 o, V3 d, unsigned vmask, Hit &best) {
+// `unit_dir`: the lane's direction has unit length (every ray the integrator generates).  The gate's origin-inside shortcut
+// (sphere_gate, r2_inside) is derived for |d| = 1; a caller-supplied ray of another length (ptb_intersect) gets the exact gate.
+__device__ __forceinline__ void closest_hit_loose(const float4 *__restrict__ s_obj, V3 o, V3 d, unsigned vmask, Hit &best,
+                                                  bool unit_dir = true) {
     const float4 *rec = s_obj;
     for (;;) {
         const float4 sph = rec[0];
@@ -32,7 +35,7 @@ __device__ __forceinline__ void closest_hit_loose(const float4 *__restrict__ s_o
         }
         if (kind == KIND_END) break;
         // mesh: bounding-sphere gate first (mod.rs:267-277)
-        const bool pass = sphere_gate(xyz(sph), sph.w, o, d, mb.x);
+        const bool pass = sphere_gate(xyz(sph), sph.w, o, d, unit_dir ? mb.x : -1.0f);
         const int n_tri = __float_as_int(mb.z);
         if (n_tri == 0) {
             // one pair (a wall quad) whose gate sphere is large against the scene, marked by the host: some lane nearly always
@@ -88,12 +91,13 @@ __device__ __forceinline__ void finish_hit(const DScene &sc, const float4 *__res
 
 // `live` lanes get their closest hit; all lanes of `vmask` must call (the loose scan votes)
 template <bool HAS_BVH>
-__device__ __forceinline__ Hit closest_hit(const DScene &sc, const float4 *__restrict__ s_obj, V3 o, V3 d, unsigned vmask, bool live) {
+__device__ __forceinline__ Hit closest_hit(const DScene &sc, const float4 *__restrict__ s_obj, V3 o, V3 d, unsigned vmask, bool live,
+                                           bool unit_dir = true) {
     Hit best;
     best.t = __int_as_float(0x7f800000);
     best.prio = PRIO_NONE;
     best.ref = REF_NONE;
-    closest_hit_loose(s_obj, o, d, vmask, best);
+    closest_hit_loose(s_obj, o, d, vmask, best, unit_dir);
     if (HAS_BVH) {
         if (live) bvh_closest_hit(sc, o, d, best);
     }

@@ -142,6 +142,22 @@ class OracleScene:
         lib().pto_intersect(self.h, _fp(rays), n, _ip(obj), _ip(tri), _fp(t), _fp(pt), _fp(nr))
         return obj, tri, t, pt, nr
 
+    def intersect_mt(self, rays: np.ndarray, threads: int | None = None):
+        """intersect() over host threads (ctypes releases the GIL; pto_intersect is re-entrant): the brute-force scan of a
+        million-triangle mesh costs ~20 ms per ray."""
+        from concurrent.futures import ThreadPoolExecutor
+        rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 6)
+        n = rays.shape[0]
+        threads = max(1, min(threads or os.cpu_count() or 1, max(n // 16, 1)))
+        if threads == 1:
+            return self.intersect(rays)
+        # small interleaved chunks: the cost per ray varies by orders of magnitude (gate miss vs full scan)
+        step = max(16, min(512, n // (threads * 8)))
+        chunks = [(i, min(i + step, n)) for i in range(0, n, step)]
+        with ThreadPoolExecutor(threads) as ex:
+            parts = list(ex.map(lambda c: self.intersect(rays[c[0]:c[1]]), chunks))
+        return tuple(np.concatenate([p[k] for p in parts], 0) for k in range(5))
+
     def primary_rays(self, W: int, H: int):
         r = np.empty((W * H, 6), np.float32)
         lib().pto_primary_rays(self.h, W, H, _fp(r))

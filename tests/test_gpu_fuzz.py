@@ -42,6 +42,10 @@ def random_scene(rng, out_dir, idx, n_spheres, n_inline, n_file_tris):
         objs.append({"type_": {"Mesh": {"triangles": tris, "bounding_sphere": {"position": [float(x) for x in centre], "radius": rad},
                                         "bounding_box": bb}},
                      "position": [float(x) for x in rng.uniform(-1, 1, 3)], "material": material(emissive=(i % 3 == 0))})
+    if idx % 2 == 0:  # a mesh without triangles (never hit; must not disturb the scene stream)
+        bb = [{"a": [0.0, 0.0, 0.0], "b": [0.0, 0.0, 0.0], "c": [0.0, 0.0, 0.0]}] * 12
+        objs.append({"type_": {"Mesh": {"triangles": [], "bounding_sphere": {"position": [0.0, 0.0, 0.0], "radius": 30.0}, "bounding_box": bb}},
+                     "position": [0.0, 0.0, 0.0], "material": material()})
     if n_file_tris:
         off = os.path.join(out_dir, "meshes", f"fuzz{idx}.off")
         os.makedirs(os.path.dirname(off), exist_ok=True)

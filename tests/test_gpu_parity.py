@@ -130,10 +130,11 @@ def test_batch_and_offset_invariance(be):
 
 
 # ---- (4) images against the reference's own behaviour (sequential RNG, libm sin/cos, recursive radiance) ----
-@pytest.mark.parametrize("sid,W,H,spp", [("cornell", 120, 80, 256), ("three-spheres", 120, 80, 64), ("mesh", 60, 40, 64)])
+@pytest.mark.parametrize("sid,W,H,spp", [("cornell", 120, 80, 1024), ("three-spheres", 120, 80, 256), ("mesh", 96, 64, 512)])
 def test_image_statistics_match_reference_mode(be, sid, W, H, spp):
     """Stated tolerance: per channel RMSE(gpu, ref) <= 1.25 * RMSE(ref_seedA, ref_seedB) and
-    |mean_gpu - mean_ref| / mean_ref <= 1 % at equal spp (unclamped means)."""
+    |mean_gpu - mean_ref| / mean_ref <= 0.5 % at equal spp (unclamped means).  The sample counts are sized so that 0.5 % is
+    about four standard deviations of the difference of two independent image means (3-10 M samples per image)."""
     import path_tracer_rust_b200.api as A
     _, osc = load_both(be, sid)
     g = be.render(W, H, spp, seed=1, out_kind=A.PTB_OUT_SUM) / f32(spp)
@@ -146,7 +147,7 @@ def test_image_statistics_match_reference_mode(be, sid, W, H, spp):
         assert err <= 1.25 * noise + 1e-7, (sid, c, err, noise)
         m_ref = 0.5 * (float(ra[:, c].mean()) + float(rb[:, c].mean()))
         if m_ref > 1e-4:
-            assert abs(float(g[:, c].mean()) - m_ref) / m_ref <= 0.01, (sid, c)
+            assert abs(float(g[:, c].mean()) - m_ref) / m_ref <= 0.005, (sid, c, float(g[:, c].mean()), m_ref)
 
 
 def test_exact_images(be):

@@ -158,6 +158,34 @@ def test_flattened_stream_matches_oracle(scene, n, quad_min_ratio):
     assert (want[0] >= 0).sum() > 500          # (open scenes: most random rays miss)
 
 
+def test_empty_mesh_is_dropped_from_the_stream(tmp_path):
+    """a mesh with zero triangles (inline `triangles: []`) used to be written with n_tri = 0, the marker of a vote-free
+    wall quad, and desynchronised the walk.  The reference renders it as no hit (mod.rs:558 loops zero times)."""
+    import json
+    import path_tracer_rust_b200 as P
+    base = json.load(open(os.path.join(ROOT, "scenes", "cornell.json")))
+    empty = {"type_": {"Mesh": {"triangles": [], "bounding_sphere": {"position": [0.0, 0.0, 0.0], "radius": 50.0},
+                                "bounding_box": base["objects"][-1]["type_"]["Mesh"]["bounding_box"]}},
+             "position": [0.0, 0.0, 0.0], "material": base["objects"][0]["material"]}
+    objs = list(base["objects"])
+    objs.insert(2, empty)          # between spheres
+    objs.insert(len(objs) - 2, dict(empty, position=[1.0, 0.0, 0.0]))   # between walls
+    objs.append(dict(empty, position=[2.0, 0.0, 0.0]))                  # first in the reference's (reverse) scan order
+    path = tmp_path / "empty_mesh.json"
+    json.dump({"id": "empty_mesh", "objects": objs, "camera": base["camera"]}, open(path, "w"))
+    sc = P.Scene.load(str(path), base_dir=ROOT)
+    osc = O.OracleScene(str(path), ROOT)
+    for ratio in (0.125, 0.0, 1e9):
+        stream, tris = sc.flatten_loose(ratio)
+        rays = _rays(osc, np.random.default_rng(11), 30_000)
+        want = osc.intersect(rays)
+        got = walk_stream(stream, tris, rays)
+        for name, a, b in zip(("obj", "tri", "t", "point", "normal"), got, want):
+            same = (bits(a) == bits(b)) if a.dtype == f32 else (a == b)
+            assert same.all(), (ratio, name, int((~same).sum()))
+        assert (want[0] >= 0).sum() > 500
+
+
 def test_quad_flag_follows_the_ratio():
     import path_tracer_rust_b200 as P
     sc = P.Scene.load("cornell")

@@ -67,10 +67,10 @@ def write_off(path: str, v: np.ndarray, f: np.ndarray):
         np.savetxt(fh, np.concatenate([np.full((len(f), 1), 3, np.int64), f], 1), fmt="%d")
 
 
-def make_synthetic(out_dir: str, level: int = 8, n_spheres: int = 10000, scale: float = 4.0, mesh_radius: float | None = None,
+def make_synthetic(out_dir: str, level: int = 8, n_spheres: int = 10000, scale: float = 10.0, mesh_radius: float | None = None,
                    seed: int = 1, scene_id: str | None = None) -> str:
     S = float(scale)
-    scene_id = scene_id or f"synthetic_l{level}_s{n_spheres}"
+    scene_id = scene_id or f"synthetic_l{level}_s{n_spheres}_x{S:g}"
     off_rel = f"meshes/icosphere_l{level}.off"
     off_path = os.path.join(out_dir, off_rel)
     if not os.path.exists(off_path):
@@ -121,7 +121,7 @@ if __name__ == "__main__":
     ap.add_argument("out_dir")
     ap.add_argument("--level", type=int, default=8)
     ap.add_argument("--spheres", type=int, default=10000)
-    ap.add_argument("--scale", type=float, default=4.0)
+    ap.add_argument("--scale", type=float, default=10.0)
     ap.add_argument("--seed", type=int, default=1)
     a = ap.parse_args()
     print(make_synthetic(a.out_dir, a.level, a.spheres, a.scale, seed=a.seed))

@@ -12,6 +12,14 @@ pinned host memory inside the timed region.
 
 `--impl reference` times the CPU path (the strict-fp32 C restatement in oracle/; the Rust reference cannot be built in this
 image) on a bounded sample of the same workload, on rank 0 only.
+
+Besides the headline line's own keys the JSON line carries
+  "extra_workloads": the other BASELINE.json configs measured in the same run (C1 cornell 450x300x100 with an un-extrapolated
+                     CPU time of the whole frame, C2 sphere scenes, C3 mesh.json 1080p x 1024, C5 the synthetic 1.31 M-triangle scene
+                     4K x 1024), each with value, e2e, roofline and clocks; at N > 1 they are sharded over the ranks like the headline;
+  "cabi_multi":      (N > 1) the headline workload once more through ptb_create_multi -- ONE process, one context, N GPUs, no torch on
+                     the data path -- driven by rank 0 while the other ranks wait.
+`--extras none` (or a comma list of workload names) limits the former, `--no-cabi-multi` skips the latter.
 """
 from __future__ import annotations
 
@@ -80,7 +88,7 @@ class ClockSampler:
         nv = self._nvml
         names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
                  0x80: "hw_power_brake_slowdown"}
-        while not self._stop.wait(0.2):
+        while not self._stop.wait(0.02):   # 20 ms: the small configs finish in tens of milliseconds
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
                 try:
@@ -135,6 +143,25 @@ def cpu_reference_run(scene_id: str, W: int, H: int, target_s: float, threads: i
                       f"{threads} threads, pixel loop only"}
 
 
+def cpu_full_frame(scene_id: str, W: int, H: int, spp: int, threads: int | None = None):
+    """The WHOLE frame on the CPU, nothing extrapolated: the oracle in the reference's own mode (sequential
+    RNG, libm sin/cos, recursive radiance, shuffled pixels) on all host threads.  Only sensible for the reference's default
+    450x300 x 100 spp frame (13.5 M samples, seconds)."""
+    import oracle_lib as O
+    threads = threads or os.cpu_count() or 1
+    path, base = resolve_scene(scene_id)
+    osc = O.OracleScene(path, base)
+    t0 = time.perf_counter()
+    _, st = osc.render_sum(W, H, spp, seed=2, rng=O.RNG_SEQ, sincos=O.SINCOS_LIBM, accum=O.ACCUM_RECURSIVE, threads=threads, shuffle=1)
+    dt = time.perf_counter() - t0
+    return {"seconds": dt, "samples": W * H * spp, "segments": int(st[0]), "mpaths_s": W * H * spp / dt * 1e-6,
+            "mseg_s": int(st[0]) / dt * 1e-6, "threads": threads,
+            "tests_per_segment": {"sphere": int(st[1]) / max(int(st[0]), 1), "gate": int(st[2]) / max(int(st[0]), 1),
+                                  "triangle": int(st[3]) / max(int(st[0]), 1)},
+            "sample": f"the whole frame: {scene_id}.json {W}x{H} x {spp} spp in {dt:.2f} s on {threads} threads (C port of the rayon path, "
+                      "pixel loop only, nothing extrapolated)"}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -159,6 +186,16 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+EXTRAS = {
+    # name: (warm-up frames, warm-up spp (0 = full), timed frames, e2e frames)
+    "cornell_default": (3, 0, 20, 5),
+    "single_sphere_1080p": (3, 0, 20, 5),
+    "three_spheres_1080p": (3, 0, 20, 5),
+    "mesh_1080p": (1, 0, 3, 1),
+    "synthetic4k": (1, 32, 2, 1),        # 45 s per 1024-spp frame on one GPU: the warm-up frame is a short one
+}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -168,6 +205,9 @@ def main():
     ap.add_argument("--workload", default="cornell4k", choices=sorted(WORKLOADS))
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (development only; recorded in config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--extras", default=None, help="'all', 'none' or a comma list of workloads measured beside the headline "
+                    "(default: all for the default headline workload at full spp, none otherwise)")
+    ap.add_argument("--no-cabi-multi", action="store_true", help="N > 1: skip the single-process ptb_create_multi measurement")
     ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
                     help="backend option (ptb_set_option), development only; recorded in config")
     ap.add_argument("--reduce", default="peer", choices=["peer", "nccl"],
@@ -184,7 +224,7 @@ def main():
     import numpy as np
     import torch
     import path_tracer_rust_b200 as P
-    from path_tracer_rust_b200.distributed import CudaShardRenderer, PeerMemoryFrame, render_sharded, shard_samples
+    from path_tracer_rust_b200.distributed import CudaShardRenderer, PeerMemoryFrame, render_sharded
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the backend has no CPU fallback (use --impl reference for the CPU path)")
@@ -197,173 +237,173 @@ def main():
     else:
         dist = None
 
-    scene_id, W, H, spp = WORKLOADS[args.workload]
-    reduced = bool(args.spp)
-    if args.spp:
-        spp = args.spp
-    scene_path, scene_base = resolve_scene(scene_id, rank)
-    scene = P.Scene.load(scene_path, base_dir=scene_base)
     be = P.Backend(local_rank)
     for kv in args.opt:
         name, _, value = kv.partition("=")
         be.set_option(name, float(value))
-    be.upload_scene(scene)
-    use_peer = world > 1 and args.reduce == "peer"
-    frame = None
-    if use_peer:
-        # CUDA IPC needs every rank to see every peer; if any rank cannot set it up, all ranks fall back to the NCCL reduce
-        ok = 1
-        try:
-            frame = PeerMemoryFrame(be, W, H, seed=2026, rank=rank, world_size=world)
-        except Exception as exc:  # noqa: BLE001
-            print(f"[rank {rank}] peer-memory frame unavailable ({exc}); falling back to NCCL", file=sys.stderr, flush=True)
-            ok = 0
-        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if int(flag.item()) == 0:
-            frame = None
-            use_peer = False
-    shard = CudaShardRenderer(be, W, H, seed=2026, device=dev) if not use_peer else None
-    nfl = W * H * 3
-    host_img = torch.empty(nfl, dtype=torch.float32).pin_memory() if rank == 0 else None
     l2_flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    peaks = load_peaks()
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    fp32_peak = sms * 128 * peaks["sm_max_mhz"] * 1e6 * 1e-12          # T lane-ops/s, un-fused (FMA is barred by parity)
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_resident():
+    def measure(workload: str, spp_override: int, warmup: int, warmup_spp: int, steps: int, e2e_steps: int, cpu_mode: str):
+        """One workload on all ranks: `warmup` untimed frames, `steps` frames timed with CUDA events (scene resident, L2 flushed
+        between frames, max over ranks), `e2e_steps` frames through the host API (scene upload + render + reduce + resolve + D2H).
+        cpu_mode: 'sample' = bounded CPU sample (cpu_reference_run), 'frame' = the whole frame on the CPU, 'none'."""
+        scene_id, W, H, spp = WORKLOADS[workload]
+        reduced = bool(spp_override)
+        if spp_override:
+            spp = spp_override
+        scene_path, scene_base = resolve_scene(scene_id, rank)
+        scene = P.Scene.load(scene_path, base_dir=scene_base)
+        be.upload_scene(scene)
+        use_peer = world > 1 and args.reduce == "peer"
+        frame = None
         if use_peer:
-            return frame.render(spp, to_host=False)
-        return render_sharded(shard, spp, rank, world)
+            # CUDA IPC needs every rank to see every peer; if any rank cannot set it up, all ranks fall back to the NCCL reduce
+            ok = 1
+            try:
+                frame = PeerMemoryFrame(be, W, H, seed=2026, rank=rank, world_size=world)
+            except Exception as exc:  # noqa: BLE001
+                print(f"[rank {rank}] peer-memory frame unavailable ({exc}); falling back to NCCL", file=sys.stderr, flush=True)
+                ok = 0
+            flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                frame = None
+                use_peer = False
+        shard = CudaShardRenderer(be, W, H, seed=2026, device=dev) if not use_peer else None
+        nfl = W * H * 3
+        host_img = torch.empty(nfl, dtype=torch.float32).pin_memory() if rank == 0 else None
+        host_np = host_img.numpy().reshape(-1, 3) if rank == 0 else None
 
-    host_np = host_img.numpy().reshape(-1, 3) if rank == 0 else None
+        def step_resident(n_spp):
+            if use_peer:
+                return frame.render(n_spp, to_host=False)
+            return render_sharded(shard, n_spp, rank, world)
 
-    def step_e2e():
-        be.upload_scene(scene)                       # H2D of the scene (flatten + upload + device BVH build)
-        if world == 1:
-            # the reference-facing call itself: ptb_render() with a HOST output buffer (here pinned), blocking like render()
-            be.render(W, H, spp, seed=2026, out=host_np)
-            return float(host_np[0, 0])
-        if use_peer:
-            frame.render(spp, host_out=host_np)      # reduce + resolve over peer memory, then D2H on rank 0
-            return float(host_np[0, 0]) if rank == 0 else None
-        img = render_sharded(shard, spp, rank, world)
-        if rank == 0:
-            host_img.copy_(img, non_blocking=True)   # D2H of the resolved image
-            torch.cuda.current_stream().synchronize()
-            return float(host_img[0])
-        return None
+        def step_e2e():
+            be.upload_scene(scene)                       # H2D of the scene (flatten + upload + device BVH build)
+            if world == 1:
+                # the reference-facing call itself: ptb_render() with a HOST output buffer (here pinned), blocking like render()
+                be.render(W, H, spp, seed=2026, out=host_np)
+                return
+            if use_peer:
+                frame.render(spp, host_out=host_np)      # reduce + resolve over peer memory, then D2H on rank 0
+                return
+            img = render_sharded(shard, spp, rank, world)
+            if rank == 0:
+                host_img.copy_(img, non_blocking=True)   # D2H of the resolved image
+                torch.cuda.current_stream().synchronize()
 
-    # ---- warm-up -------------------------------------------------------------------------------------------------
-    for _ in range(max(args.warmup, 0)):
-        step_resident()
-    barrier()
-
-    # ---- timed: K steps, CUDA events on the launching stream, L2 flushed between steps ------------------------------
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    seg_total, launches = 0, 0
-    times = []
-    for _ in range(args.steps):
-        l2_flush.fill_(1.0)
+        for _ in range(max(warmup, 0)):
+            step_resident(warmup_spp or spp)
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        step_resident()
-        e1.record()
-        torch.cuda.synchronize()
-        times.append(e0.elapsed_time(e1))
-        st = be.stats()
-        seg_total += st["segments"]
-        launches += st["kernel_launches"] + (1 if (rank == 0 or use_peer) else 0)
-    barrier()
-    clocks = sampler.stop()
-    kernel_ms_last = be.stats()["render_ms"]
-
-    # ---- e2e through the host API ------------------------------------------------------------------------------------
-    e2e_times = []
-    e2e_steps = max(1, min(args.steps, 2))      # the resident steps above already warmed the device up
-    for _ in range(e2e_steps):
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        seg_total, launches, times = 0, 0, []
+        for _ in range(steps):
+            l2_flush.fill_(1.0)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step_resident(spp)
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+            st = be.stats()
+            seg_total += st["segments"]
+            launches += st["kernel_launches"] + (1 if (rank == 0 or use_peer) else 0)
         barrier()
-        t0 = time.perf_counter()
-        step_e2e()
-        torch.cuda.synchronize()
-        e2e_times.append((time.perf_counter() - t0) * 1e3)
-    barrier()
+        clocks = sampler.stop()
+        st_last = be.stats()
+        kernel_ms_last = st_last["render_ms"]
+        e2e_times = []
+        for _ in range(e2e_steps):
+            barrier()
+            t0 = time.perf_counter()
+            step_e2e()
+            torch.cuda.synchronize()
+            e2e_times.append((time.perf_counter() - t0) * 1e3)
+        barrier()
+        t_sum = torch.tensor([sum(times), sum(e2e_times), float(seg_total), float(launches)], dtype=torch.float64, device=dev)
+        if dist is not None:
+            t_max = t_sum.clone()
+            dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t_sum, op=dist.ReduceOp.SUM)
+            total_ms, e2e_ms = float(t_max[0]), float(t_max[1])
+            seg_total, launches = float(t_sum[2]), int(t_sum[3])
+        else:
+            total_ms, e2e_ms = float(t_sum[0]), float(t_sum[1])
+        if frame is not None:
+            frame.close()
+        if rank != 0:
+            return None
 
-    t_sum = torch.tensor([sum(times), sum(e2e_times), float(seg_total), float(launches)], dtype=torch.float64, device=dev)
-    if dist is not None:
-        t_max = t_sum.clone()
-        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
-        dist.all_reduce(t_sum, op=dist.ReduceOp.SUM)
-        total_ms, e2e_ms = float(t_max[0]), float(t_max[1])
-        seg_total, launches = float(t_sum[2]), int(t_sum[3])
-    else:
-        total_ms, e2e_ms = float(t_sum[0]), float(t_sum[1])
-
-    if rank == 0:
-        peaks = load_peaks()
         samples_per_step = W * H * spp
-        value = samples_per_step * args.steps / (total_ms * 1e-3) * 1e-6
+        value = samples_per_step * steps / (total_ms * 1e-3) * 1e-6
         seg_rate = seg_total / (total_ms * 1e-3) * 1e-6
-        e2e_value = samples_per_step * e2e_steps / (e2e_ms * 1e-3) * 1e-6
+        e2e_value = samples_per_step * e2e_steps / (e2e_ms * 1e-3) * 1e-6 if e2e_steps else None
         sd = scene._desc.contents
         scene_bytes = int(sd.n_objects) * 80 + int(sd.n_triangles) * 36 + 36
         cpu = None
-        if not args.no_cpu_baseline and world == 1:
+        if cpu_mode == "sample" and world == 1:
             cpu = cpu_reference_run(scene_id, W, H, 12.0)
-        # roofline of the dominant kernel (k_render): FP32 issue slots.  Algorithmic flops per segment follow SURVEY.md 8d:
-        # 17 per sphere/gate test + 45 per triangle test + 120 shading, with the reference algorithm's own test counts.
-        st_last = be.stats()
+        elif cpu_mode == "frame" and world == 1:
+            cpu = cpu_full_frame(scene_id, W, H, spp)
+        # roofline of the dominant kernel: FP32 issue slots.  Algorithmic flops per segment follow SURVEY.md 8d:
+        # 17 per sphere/gate test + 45 per triangle test + 30 per four-wide BVH node + 120 shading, with the reference algorithm's
+        # own test counts for the shared-memory list and device-counted BVH work.
         if st_last["n_bvh_nodes"] > 0 and st_last["segments"] > 0:
-            # BVH scene: device-counted work of the last step (wavefront integrator): every segment scans the shared-memory list,
-            # then visits bvh_nodes_visited inner nodes (30 flops each: two slab tests) and tests bvh_prims_tested primitives
             seg_last = float(st_last["segments"])
             tps = {"sphere": 0.0, "gate": float(st_last["n_loose_objects"]),
                    "triangle": float(st_last["n_loose_triangles"]) + st_last["bvh_prims_tested"] / seg_last,
                    "bvh_nodes": st_last["bvh_nodes_visited"] / seg_last}
             dominant = "k_wf_trace (+ k_wf_shade, k_wf_generate, k_wf_accumulate; whole wavefront pipeline timed)"
         else:
-            tps = cpu["tests_per_segment"] if cpu else None
+            tps = cpu["tests_per_segment"] if cpu and "tests_per_segment" in cpu else None
             if tps is None:
                 tps = {"sphere": 4.0, "gate": 7.0, "triangle": 11.0} if scene_id == "cornell" else {"sphere": 0, "gate": 0, "triangle": 0}
             tps = dict(tps, bvh_nodes=0.0)
-            dominant = "k_render"
+            dominant = "k_render" if not (W * H < 2 * sms * 24 * 32) else "k_wf_shade (+ k_wf_generate, k_wf_accumulate: wavefront integrator, small frame)"
         flops_per_seg = 17.0 * (tps["sphere"] + tps["gate"]) + 45.0 * tps["triangle"] + 30.0 * tps["bvh_nodes"] + 120.0
-        # secondary (HBM) view for BVH scenes, SURVEY.md 8d: 32 B per box tested (4 per node visit), 48 B per primitive, ray state in
-        # and out of the HBM queues (4 x float4 + 12 B hit, read by trace + shade, written by shade)
+        # secondary (HBM) view for BVH scenes: queue entries written by generate / shade (76 B), read by trace (44 B of the
+        # segments that reach the BVH: counted as all) and by shade (72 B), hit written back by trace (8 B); BVH nodes and
+        # primitives are L2-resident and not counted
         hbm = None
         if tps["bvh_nodes"] > 0:
-            bytes_per_seg = 128.0 * tps["bvh_nodes"] + 48.0 * (tps["triangle"] - float(st_last["n_loose_triangles"])) + 2 * 76.0 + 44.0
-            gbs = seg_total / max(world, 1) / args.steps * bytes_per_seg / (kernel_ms_last * 1e-3) * 1e-9 if kernel_ms_last > 0 else None
+            bytes_per_seg = 76.0 + 44.0 + 72.0 + 8.0
+            gbs = seg_total / max(world, 1) / steps * bytes_per_seg / (kernel_ms_last * 1e-3) * 1e-9 if kernel_ms_last > 0 else None
             hbm = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"] if gbs else None,
                    "bytes_per_segment": bytes_per_seg,
-                   "note": "upper bound on DRAM traffic: the BVH is L2-resident (ncu: lts hit rate ~80 %), so this path is not HBM bound"}
-        sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        fp32_peak = sms * 128 * peaks["sm_max_mhz"] * 1e6 * 1e-12          # T lane-ops/s, un-fused (FMA is barred by parity)
-        seg_per_gpu = seg_total / max(world, 1) / args.steps
+                   "note": "queue traffic only (algorithmic bytes per ray segment); BVH nodes / primitives are served from L2"}
+        seg_per_gpu = seg_total / max(world, 1) / steps
         kern_s = kernel_ms_last * 1e-3
         achieved = seg_per_gpu * flops_per_seg / kern_s * 1e-12 if kern_s > 0 else None
         traffic, ncu_note = None, None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath) and not reduced:
-            tj = json.load(open(tpath)).get(args.workload)
+            tj = json.load(open(tpath)).get(workload)
             if tj:
                 traffic, ncu_note = tj["dram_bytes_per_launch"], {k: tj[k] for k in ("kernel", "launch", "algorithmic_bytes_per_launch", "ncu", "source")}
-        line = {
-            "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms / max(args.steps, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        return {
+            "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": total_ms / max(steps, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: scenes/{scene_id}.json {W}x{H} x {spp} spp, spp sharded over {world} GPU(s), "
+            "config": {"workload": f"{workload}: scenes/{scene_id}.json {W}x{H} x {spp} spp, spp sharded over {world} GPU(s), "
                                    + ("fused peer-memory reduce+resolve kernel over NVLink (CUDA IPC)" if use_peer
                                       else ("NCCL fp32 sum-reduce" if world > 1 else "no reduce step")), "scene": scene_id, "width": W, "height": H, "spp": spp,
                        "spp_reduced_for_development": reduced, "l2": "flushed between steps (256 MiB device write)",
-                       "parallelism": f"spp-shard x{world}", "backend_options": list(args.opt)},
-            "mray_segments_per_s": seg_rate, "segments_per_sample": seg_total / (samples_per_step * args.steps),
+                       "parallelism": f"spp-shard x{world}", "backend_options": list(args.opt),
+                       "warmup_spp": warmup_spp or spp},
+            "mray_segments_per_s": seg_rate, "segments_per_sample": seg_total / (samples_per_step * steps),
             "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": scene_bytes, "d2h_bytes_per_step": nfl * 4,
-                    "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps},
+                    "ms_per_step": e2e_ms / e2e_steps if e2e_steps else None, "steps": e2e_steps},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "fp32_issue", "achieved": achieved, "peak": fp32_peak, "unit": "Tlane-op/s",
@@ -375,9 +415,71 @@ def main():
             "cpu_baseline": ({"value": cpu["mpaths_s"], "unit": "Mpaths/s", "cores": cpu["threads"], "kind": "port",
                               "sample": cpu["sample"], "mray_segments_per_s": cpu["mseg_s"]} if cpu else None),
         }
+
+    # ---- headline -----------------------------------------------------------------------------------------------------
+    e2e_steps = max(1, min(args.steps, 2))      # the resident steps already warmed the device up
+    line = measure(args.workload, args.spp, args.warmup, 0, args.steps, e2e_steps, "none" if args.no_cpu_baseline else "sample")
+
+    # ---- the other BASELINE configs, same run ---------------------------------------------------------------------------
+    if args.extras is None:
+        extras = [w for w in EXTRAS if w != args.workload] if (args.workload == "cornell4k" and not args.spp) else []
+    elif args.extras in ("none", ""):
+        extras = []
+    elif args.extras == "all":
+        extras = [w for w in EXTRAS if w != args.workload]
+    else:
+        extras = [w for w in args.extras.split(",") if w in EXTRAS]
+    extra_lines = {}
+    for w in extras:
+        wu, wu_spp, k, ke = EXTRAS[w]
+        t0 = time.perf_counter()
+        try:
+            r = measure(w, 0, wu, wu_spp, k, ke, "frame" if (w == "cornell_default" and not args.no_cpu_baseline) else "none")
+        except Exception as exc:  # noqa: BLE001  (an extra must never take the headline down)
+            r = {"error": f"{type(exc).__name__}: {exc}"} if rank == 0 else None
+        if rank == 0:
+            r["wall_s"] = time.perf_counter() - t0
+            extra_lines[w] = r
+
+    # ---- N > 1: the same frame through ONE process and ONE context (ptb_create_multi), rank 0 drives all GPUs -------------
+    cabi = None
+    if world > 1 and not args.no_cabi_multi:
+        barrier()
+        if rank == 0:
+            try:
+                scene_id, W, H, spp = WORKLOADS[args.workload]
+                spp = args.spp or spp
+                scene_path, scene_base = resolve_scene(scene_id, rank)
+                scene = P.Scene.load(scene_path, base_dir=scene_base)
+                mb = P.Backend(list(range(world)))
+                for kv in args.opt:
+                    name, _, value = kv.partition("=")
+                    mb.set_option(name, float(value))
+                host = torch.empty(W * H * 3, dtype=torch.float32).pin_memory().numpy().reshape(-1, 3)
+                mb.upload_scene(scene)
+                mb.render(W, H, max(spp // 8, world), seed=2026, out=host)           # warm-up: allocations, clocks
+                ts = []
+                for _ in range(2):
+                    t0 = time.perf_counter()
+                    mb.upload_scene(scene)
+                    mb.render(W, H, spp, seed=2026, out=host)
+                    ts.append(time.perf_counter() - t0)
+                st = mb.stats()
+                cabi = {"value": W * H * spp / min(ts) * 1e-6, "unit": "Mpaths/s", "ms_per_step": min(ts) * 1e3, "steps": 2, "n_gpus": world,
+                        "device_ms_slowest_gpu": st["render_ms"], "gpu_launches": st["kernel_launches"],
+                        "how": "ptb_create_multi + ptb_upload_scene + ptb_render from rank 0's process: one host thread per GPU, "
+                               "spp split by global sample index, fused peer-memory reduce+resolve, D2H to pinned host memory; "
+                               "wall clock around the calls (end to end), best of 2"}
+                mb.close()
+            except Exception as exc:  # noqa: BLE001
+                cabi = {"error": f"{type(exc).__name__}: {exc}"}
+        barrier()
+
+    if rank == 0:
+        line["extra_workloads"] = extra_lines
+        if cabi is not None:
+            line["cabi_multi"] = cabi
         print(json.dumps(line), flush=True)
-    if frame is not None:
-        frame.close()
     if dist is not None:
         dist.destroy_process_group()
     be.close()

@@ -11,8 +11,10 @@
  * Conventions: plain C types only; return 0 = PTB_OK, <0 = error (message via ptb_last_error),
  * PTB_CANCELLED (1) = stopped early by the cancel flag.  Nothing throws or aborts across the
  * boundary.  The caller owns every host buffer it passes; the library owns all device memory
- * behind the opaque ptb_ctx.  One ctx = one CUDA device, used from one host thread at a time
- * (multi-GPU = one process / one ctx per GPU, framebuffers summed by the caller's collective).
+ * behind the opaque ptb_ctx.  A ctx is used from one host thread at a time.  ptb_create gives one CUDA device;
+ * ptb_create_multi gives a context that drives several devices of one box from this process (samples per pixel split
+ * across them, one internal host thread per device, framebuffers summed over NVLink peer memory inside ptb_render).
+ * One process per GPU with the caller's own collective works too (ptb_render_device + ptb_peer_reduce_resolve / NCCL).
  * There is NO CPU fallback: every compute entry point fails with PTB_ERR_CUDA without a device.
  */
 #ifndef PTB_H
@@ -33,7 +35,7 @@ extern "C" {
 #define PTB_ERR_STATE (-5)
 #define PTB_ERR_LIMIT (-6)
 
-#define PTB_ABI_VERSION 1
+#define PTB_ABI_VERSION 2
 
 typedef struct ptb_ctx ptb_ctx;     /* device context: streams, scene buffers, BVH, framebuffer */
 typedef struct ptb_scene ptb_scene; /* host-side scene loaded from scenes/<id>.json (+ OFF meshes) */
@@ -106,6 +108,14 @@ void ptb_scene_free(ptb_scene *scene);
 int ptb_abi_version(void);
 int ptb_device_count(void);
 int ptb_create(int device_id, ptb_ctx **out);
+/* Multi-GPU inside the library (the seam is still render(), mod.rs:928-934 / main.rs:364 / cmd_render.rs:17-44: one call, all GPUs).
+ * The context drives device_ids[0..n_devices): ptb_upload_scene replicates the scene (and builds the BVH) on every device,
+ * ptb_set_option applies to all, ptb_render / ptb_render_progressive render global sample indices
+ * [spp_begin + g*spp_count/n, spp_begin + (g+1)*spp_count/n) on device g and sum the framebuffers in device order with the
+ * fused peer-memory reduce+resolve kernel, ptb_get_stats reports the whole job.  The parity hooks (ptb_primary_hits, ptb_intersect)
+ * run on device_ids[0].  n_devices = 1 is the same as ptb_create. */
+int ptb_create_multi(const int *device_ids, int n_devices, ptb_ctx **out);
+int ptb_device_ids(const ptb_ctx *ctx, int *ids, int cap); /* returns the number of devices the context drives */
 void ptb_destroy(ptb_ctx *ctx);
 const char *ptb_last_error(const ptb_ctx *ctx); /* ctx may be NULL: last error of the calling thread */
 
@@ -121,11 +131,10 @@ int ptb_flatten_loose(const ptb_scene_desc *desc, double quad_min_ratio, float *
 /* Tuning knobs, effective from the next ptb_upload_scene (results never depend on them, only speed):
  *   "bvh_min_tris"    meshes with at least this many triangles are traversed through the BVH (default 24; a huge value = brute force)
  *   "bvh_min_spheres" scenes with at least this many spheres put them in the BVH (default 48)
- *   "integrator"      0 = auto (wavefront when the scene has a BVH, else megakernel), 1 = megakernel, 2 = wavefront
- *   "wavefront_paths" ray segments in flight per wavefront batch (default 2^23)
- *   "bvh_leaf_max" (1..8, default 2), "wf_refill", "wf_descend_min", "wf_coop" (experimental four-lanes-per-ray trace kernel,
- *   default 0), "wf_sort" (trace bounce >= 1 in octant/Morton-cell order: 0 off = default, 1, 2; measured slower): traversal
- *   tuning, see DESIGN.md
+ *   "integrator"      0 = auto (wavefront when the scene has a BVH or the frame is small, else megakernel), 1 = megakernel, 2 = wavefront
+ *   "wavefront_paths" paths in flight per wavefront batch (default 2^25; the workspace is 0.7 KB per path)
+ *   "bvh_leaf_max" (1..8, default 2), "bvh_top_levels" (0..5: four-wide levels the trace kernel keeps in shared memory),
+ *   "wf_refill", "wf_descend_min", "wf_trace_threads" (256 / 512 / 1024): traversal tuning, see DESIGN.md
  *   "quad_min_ratio"  a two-triangle mesh whose bounding-sphere radius is at least this fraction of the scene diagonal is tested
  *                     without the per-mesh warp vote (default 0.125; 0 = every two-triangle mesh, a huge value = none)
  *   "regen_batch"     lanes that must be waiting for a camera ray before the ray-generation code runs (default 24) */
@@ -140,10 +149,22 @@ int ptb_selftest(ptb_ctx *ctx, uint64_t *mismatches);
  *   PTB_OUT_MEAN : sum / spp_count clamped to [0,1]  == Image.pixels (mod.rs:849-856)
  *   PTB_OUT_SUM  : raw fp32 radiance sum (for spp-sharded multi-GPU / progressive use; add, then resolve)
  * `cancel` (may be NULL) is polled between launches like stop_render (mod.rs:1003); `samples_done` (may be NULL)
- * receives pixel-samples finished so far (processed_pixel_count analogue, mod.rs:850). */
+ * receives pixel-samples finished so far (processed_pixel_count analogue, mod.rs:850).  When either is given the work per
+ * launch is capped (about 0.1-0.2 s), so a cancel takes effect and progress moves at that granularity. */
 enum { PTB_OUT_MEAN = 0, PTB_OUT_SUM = 1 };
 int ptb_render(ptb_ctx *ctx, int width, int height, uint64_t spp_begin, uint64_t spp_count, uint64_t seed,
                int out_kind, float *out_rgb, const volatile int32_t *cancel, volatile uint64_t *samples_done);
+
+/* RenderUpdate{progress, image} (mod.rs:882-886, sent about every 500 ms by mod.rs:965-982 and drawn by views/render_tab.rs:278-297):
+ * ptb_render_progressive is ptb_render that also hands the caller the image so far.  Between launches, once `preview_interval_ms`
+ * have passed since the last preview, the partial sum is resolved (mean of the samples finished so far, clamped) and `on_preview`
+ * is called on the rendering thread with a library-owned host buffer that is valid during the call only; spp_done / spp_total is
+ * the progress.  The final image arrives through out_rgb exactly as with ptb_render (bit-identical to an unpreviewed render).
+ * On a multi-GPU context the previews show device 0's share of the samples. */
+typedef void (*ptb_preview_fn)(void *user, const float *mean_rgb, int width, int height, uint64_t spp_done, uint64_t spp_total);
+int ptb_render_progressive(ptb_ctx *ctx, int width, int height, uint64_t spp_begin, uint64_t spp_count, uint64_t seed,
+                           int out_kind, float *out_rgb, const volatile int32_t *cancel, volatile uint64_t *samples_done,
+                           double preview_interval_ms, ptb_preview_fn on_preview, void *user);
 
 /* Same, accumulating into a caller-provided DEVICE sum framebuffer (W*H*3 fp32, += in sample order) on
  * `cuda_stream` (a cudaStream_t; NULL = the default stream).  Asynchronous unless cancel/samples_done is given. */

@@ -71,7 +71,9 @@ ABI_SYMBOLS = ["ptb_scene_load_json", "ptb_scene_load_json_ex", "ptb_scene_save_
                "ptb_render", "ptb_render_device", "ptb_resolve_device", "ptb_primary_hits", "ptb_intersect",
                "ptb_to_int_with_gamma_correction", "ptb_write_ppm", "ptb_hash_pixels", "ptb_device_alloc", "ptb_device_free",
                "ptb_device_memset", "ptb_device_to_host", "ptb_device_sync", "ptb_ipc_export", "ptb_ipc_open", "ptb_ipc_close",
-               "ptb_peer_reduce_resolve", "ptb_flatten_loose"]
+               "ptb_peer_reduce_resolve", "ptb_flatten_loose", "ptb_create_multi", "ptb_device_ids", "ptb_render_progressive"]
+
+PREVIEW_FN = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_uint64, C.c_uint64)  # ptb_preview_fn
 
 
 def load_library():
@@ -96,6 +98,10 @@ def load_library():
         L.ptb_scene_id.argtypes = [C.c_void_p]
         L.ptb_scene_free.argtypes = [C.c_void_p]
         L.ptb_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.ptb_create_multi.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]
+        L.ptb_device_ids.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int]
+        L.ptb_render_progressive.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, fp,
+                                             C.POINTER(C.c_int32), C.POINTER(C.c_uint64), C.c_double, PREVIEW_FN, C.c_void_p]
         L.ptb_destroy.argtypes = [C.c_void_p]
         L.ptb_last_error.restype = C.c_char_p
         L.ptb_last_error.argtypes = [C.c_void_p]
@@ -126,7 +132,7 @@ def load_library():
         L.ptb_write_ppm.argtypes = [C.c_char_p, fp, C.c_int, C.c_int, C.c_uint64, C.c_char_p, C.c_uint64]
         L.ptb_hash_pixels.restype = C.c_uint64
         L.ptb_hash_pixels.argtypes = [fp, C.c_uint64]
-        if L.ptb_abi_version() != 1:
+        if L.ptb_abi_version() != 2:
             raise BackendError(-5, "libptb.so ABI version mismatch")
         _lib = L
         return L
@@ -300,16 +306,24 @@ class RenderDone:  # mod.rs:888-891
 
 
 class Backend:
-    """One ptb_ctx = one B200.  The context owns the device scene, BVH and framebuffer."""
+    """One ptb_ctx: one B200 (`Backend(0)`) or several GPUs of the box driven from this process (`Backend([0, 1, 2, 3])`,
+    ptb_create_multi: samples per pixel split across the devices, framebuffers summed over peer memory inside render()).
+    The context owns the device scene, BVH and framebuffer."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device=0):
         self.L = load_library()
         h = C.c_void_p()
-        rc = self.L.ptb_create(device, C.byref(h))
+        if isinstance(device, (list, tuple)):
+            ids = (C.c_int * len(device))(*device)
+            rc = self.L.ptb_create_multi(ids, len(device), C.byref(h))
+            self.devices = list(device)
+        else:
+            rc = self.L.ptb_create(device, C.byref(h))
+            self.devices = [device]
         if rc != PTB_OK:
             raise BackendError(rc, self.L.ptb_last_error(None).decode())
         self._h = h
-        self.device = device
+        self.device = self.devices[0]
         self._scene = None
 
     def close(self):
@@ -347,6 +361,23 @@ class Backend:
         cp = C.cast(C.byref(cancel), C.POINTER(C.c_int32)) if cancel is not None else None
         sp = C.cast(C.byref(samples_done), C.POINTER(C.c_uint64)) if samples_done is not None else None
         self.last_rc = self._check(self.L.ptb_render(self._h, width, height, spp_begin, spp_count, seed, out_kind, _fp(buf), cp, sp))
+        return buf
+
+    def render_progressive(self, width: int, height: int, spp_count: int, on_preview, preview_interval_ms: float = 500.0,
+                           spp_begin: int = 0, seed: int = 0, out_kind: int = PTB_OUT_MEAN, cancel=None, samples_done=None,
+                           out: Optional[np.ndarray] = None) -> np.ndarray:
+        """ptb_render_progressive: `on_preview(mean_rgb [W*H,3] copy, spp_done, spp_total)` is called between launches, at most
+        every `preview_interval_ms`, with the mean of the samples finished so far (RenderUpdate.image, mod.rs:965-982)."""
+        buf = out if out is not None else np.empty((width * height, 3), np.float32)
+        cp = C.cast(C.byref(cancel), C.POINTER(C.c_int32)) if cancel is not None else None
+        sp = C.cast(C.byref(samples_done), C.POINTER(C.c_uint64)) if samples_done is not None else None
+
+        def trampoline(_user, ptr, w, h, done, total):
+            on_preview(np.ctypeslib.as_array(ptr, shape=(w * h, 3)).copy(), int(done), int(total))
+
+        cb = PREVIEW_FN(trampoline)
+        self.last_rc = self._check(self.L.ptb_render_progressive(self._h, width, height, spp_begin, spp_count, seed, out_kind, _fp(buf),
+                                                                 cp, sp, float(preview_interval_ms), cb, None))
         return buf
 
     def render_device(self, width: int, height: int, spp_count: int, d_sum_ptr: int, spp_begin: int = 0, seed: int = 0,
@@ -446,18 +477,22 @@ def render(render_config: RenderConfig, send_update_progress: Optional[Callable[
         done = C.c_uint64(0)
         stop = threading.Event()
 
-        def watcher():  # the reference's two helper threads (cancel watcher + progress reporter)
-            while not stop.wait(min(0.1, progress_interval)):
+        def watcher():  # the reference's cancel watcher thread (mod.rs:947-958); progress without an image in between previews
+            while not stop.wait(min(0.1, max(progress_interval, 0.01))):
                 if cancel_render is not None and cancel_render.is_set():
                     cancel.value = 1
-                if send_update_progress is not None:
-                    send_update_progress(RenderUpdate(progress=done.value / max(total, 1), image=None))
+
+        def on_preview(mean_rgb, spp_done, spp_total):  # RenderUpdate{progress, image} about every 500 ms (mod.rs:965-982)
+            if send_update_progress is not None:
+                img = Image(pixels=mean_rgb, resolution=res, hash=hash_pixels(mean_rgb))
+                send_update_progress(RenderUpdate(progress=spp_done / max(spp_total, 1), image=img))
 
         th = threading.Thread(target=watcher, daemon=True)
         th.start()
         try:
-            pixels = be.render(res.width, res.height, render_config.samples_per_pixel, seed=render_config.seed, cancel=cancel,
-                               samples_done=done)
+            pixels = be.render_progressive(res.width, res.height, render_config.samples_per_pixel, on_preview,
+                                           preview_interval_ms=progress_interval * 1e3, seed=render_config.seed, cancel=cancel,
+                                           samples_done=done)
         finally:
             stop.set()
             th.join()

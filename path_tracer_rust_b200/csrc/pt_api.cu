@@ -10,7 +10,10 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
+#include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/ptb.h"
@@ -73,14 +76,18 @@ struct ptb_ctx {
     BvhOptions bvh_opt;
     WfWorkspace wf;
     int integrator = 0;             // 0 = auto (wavefront when the scene has a BVH), 1 = megakernel, 2 = wavefront
-    double wavefront_paths = 8388608.0;  // ray segments in flight per wavefront batch
+    WfOptions wf_opt;               // wavefront integrator tuning (paths in flight, refill threshold, trace CTA size)
     int regen_batch = REGEN_BATCH;
     double quad_min_ratio = 0.125;  // one-pair meshes with gate radius >= this x scene diagonal are tested without the warp vote
-    // wf_sort: trace the rays of bounce >= 1 in (direction octant, Morton cell) order [1] or (cell, octant) order [2].  Off by
-    // default: measured slower on B200 (the sort, the read-back and the scattered ray fetch cost more than the traversal gains)
-    int wf_sort = 0;
-    int wf_refill = 8, wf_descend_min = 12, wf_coop = 0;  // wf_coop: experimental four-lanes-per-ray trace kernel (slower)
-    DevBuf<float> fb, scratch_f;
+    DevBuf<float> fb, scratch_f, preview;
+    DevBuf<int> check_word;         // PTB_CHECK build: first bounds violation seen by a kernel (0 = none)
+    float *preview_host = nullptr;  // pinned staging buffer of the progressive previews
+    size_t preview_host_floats = 0;
+    // multi-GPU context (ptb_create_multi): this context drives device_ids[0], `members` the other devices
+    std::vector<ptb_ctx *> members;
+    std::vector<float *> peer_stage;  // without peer access: copies of the members' sum framebuffers on this device
+    size_t peer_stage_floats = 0;
+    bool peer_access = false;
     DevBuf<int> scratch_i;
     DevBuf<int> tile_counter;
     DevBuf<unsigned long long> seg_counter;
@@ -184,7 +191,12 @@ extern "C" const char *ptb_last_error(const ptb_ctx *ctx) { return ctx ? ctx->er
 
 extern "C" void ptb_destroy(ptb_ctx *ctx) {
     if (!ctx) return;
+    for (ptb_ctx *m : ctx->members) ptb_destroy(m);
+    ctx->members.clear();
     cudaSetDevice(ctx->device);
+    for (float *p : ctx->peer_stage) cudaFree(p);
+    if (ctx->preview_host) cudaFreeHost(ctx->preview_host);
+    ctx->preview.release(); ctx->check_word.release();
     ctx->loose_obj.release(); ctx->loose_tri.release(); ctx->obj_gate.release(); ctx->mat_color.release();
     ctx->mat_emis.release(); ctx->fb.release(); ctx->scratch_f.release(); ctx->scratch_i.release();
     ctx->tile_counter.release(); ctx->seg_counter.release();
@@ -227,6 +239,8 @@ extern "C" int ptb_create(int device_id, ptb_ctx **out) {
     if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = ctx->tile_counter.resize(1)) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = ctx->seg_counter.resize(4)) != cudaSuccess) return bail(e, "cudaMalloc");  // segments, BVH nodes, BVH prims, -
+    if ((e = ctx->check_word.resize(1)) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMemsetAsync(ctx->check_word.p, 0, sizeof(int), ctx->stream)) != cudaSuccess) return bail(e, "cudaMemset");
     // parity self-test: the kernels must have been built with --fmad=false
     if ((e = ctx->scratch_f.resize(4)) != cudaSuccess) return bail(e, "cudaMalloc");
     const float a = 1.0f + 1.0f / 8192.0f, c = -(1.0f + 1.0f / 4096.0f);
@@ -383,8 +397,7 @@ extern "C" int ptb_flatten_loose(const ptb_scene_desc *desc, double quad_min_rat
     return PTB_OK;
 }
 
-extern "C" int ptb_upload_scene(ptb_ctx *ctx, const ptb_scene_desc *desc) {
-    if (!ctx || !desc) return fail(ctx, PTB_ERR_ARG, "ptb_upload_scene: null argument");
+static int upload_scene_one(ptb_ctx *ctx, const ptb_scene_desc *desc) {
     int code = PTB_OK;
     if (const char *why = validate_desc(desc, code)) return fail(ctx, code, std::string("ptb_upload_scene: ") + why);
     CU(ctx, cudaSetDevice(ctx->device));
@@ -430,6 +443,7 @@ extern "C" int ptb_upload_scene(ptb_ctx *ctx, const ptb_scene_desc *desc) {
     ds.obj_gate = ctx->obj_gate.p; ds.mat_color = ctx->mat_color.p; ds.mat_emis = ctx->mat_emis.p;
     ds.n_obj = static_cast<int>(nobj);
     ds.bvh_root = BVH_EMPTY_REF;
+    ds.check = ctx->check_word.p;
 
     // camera frame, once per scene like render() (mod.rs:998-999; CameraData mod.rs:211-232)
     {
@@ -464,6 +478,30 @@ extern "C" int ptb_upload_scene(ptb_ctx *ctx, const ptb_scene_desc *desc) {
     return PTB_OK;
 }
 
+// runs fn(member) for every device of a (multi-GPU) context, one host thread per device; returns the first error
+template <typename F>
+static int for_each_device(ptb_ctx *ctx, F fn) {
+    if (ctx->members.empty()) return fn(ctx, 0);
+    const size_t G = ctx->members.size() + 1;
+    std::vector<int> rc(G, PTB_OK);
+    std::vector<std::thread> th;
+    for (size_t g = 1; g < G; ++g) th.emplace_back([&, g] { rc[g] = fn(ctx->members[g - 1], (int)g); });
+    rc[0] = fn(ctx, 0);
+    for (auto &t : th) t.join();
+    for (size_t g = 0; g < G; ++g)
+        if (rc[g] < 0) {
+            if (g > 0) ctx->err = "device " + std::to_string(ctx->members[g - 1]->device) + ": " + ctx->members[g - 1]->err;
+            g_thread_error = ctx->err;
+            return rc[g];
+        }
+    return PTB_OK;
+}
+
+extern "C" int ptb_upload_scene(ptb_ctx *ctx, const ptb_scene_desc *desc) {
+    if (!ctx || !desc) return fail(ctx, PTB_ERR_ARG, "ptb_upload_scene: null argument");
+    return for_each_device(ctx, [&](ptb_ctx *m, int) { return upload_scene_one(m, desc); });  // the scene is replicated
+}
+
 extern "C" int ptb_selftest(ptb_ctx *ctx, uint64_t *mismatches) {
     if (!ctx || !mismatches) return fail(ctx, PTB_ERR_ARG, "ptb_selftest: null argument");
     CU(ctx, cudaSetDevice(ctx->device));
@@ -479,59 +517,92 @@ extern "C" int ptb_selftest(ptb_ctx *ctx, uint64_t *mismatches) {
 extern "C" int ptb_set_option(ptb_ctx *ctx, const char *key, double value) {
     if (!ctx || !key) return fail(ctx, PTB_ERR_ARG, "ptb_set_option: null argument");
     const std::string k = key;
+    for (ptb_ctx *m : ctx->members) {
+        const int rc = ptb_set_option(m, key, value);
+        if (rc != PTB_OK) return fail(ctx, rc, m->err);
+    }
     if (k == "bvh_min_tris") ctx->bvh_opt.min_tris = value;
     else if (k == "bvh_min_spheres") ctx->bvh_opt.min_spheres = value;
-    else if (k == "bvh_pad_scale_UNSAFE") ctx->bvh_opt.pad_scale = value;
     else if (k == "bvh_leaf_max") ctx->bvh_opt.leaf_max = (int)value;
-    else if (k == "wf_refill") ctx->wf_refill = (int)value;
-    else if (k == "wf_descend_min") ctx->wf_descend_min = (int)value;
-    else if (k == "wf_coop") ctx->wf_coop = (int)value;
-    else if (k == "wf_sort") ctx->wf_sort = (int)value;
+    else if (k == "bvh_top_levels") ctx->bvh_opt.top_levels = std::max(0, std::min(5, (int)value));
+    else if (k == "wf_refill") ctx->wf_opt.refill = (int)value;
+    else if (k == "wf_descend_min") ctx->wf_opt.descend_min = (int)value;
+    else if (k == "wf_trace_threads") ctx->wf_opt.trace_threads = (int)value;
     else if (k == "quad_min_ratio") ctx->quad_min_ratio = value;
     else if (k == "regen_batch") ctx->regen_batch = std::max(1, std::min(32, (int)value));
     else if (k == "integrator") ctx->integrator = (int)value;
-    else if (k == "wavefront_paths") ctx->wavefront_paths = std::max(1024.0, value);
+    else if (k == "wavefront_paths") ctx->wf_opt.target_paths = (size_t)std::max(1024.0, value);
+#ifdef PTB_EXPERIMENTS  // never in the release library: a value below 1 voids the parity guarantee (tools/pad_check.py)
+    else if (k == "bvh_pad_scale_UNSAFE") ctx->bvh_opt.pad_scale = value;
+#endif
     else return fail(ctx, PTB_ERR_ARG, "ptb_set_option: unknown key " + k);
+    return PTB_OK;
+}
+
+static int finish_pending_stats(const ptb_ctx *ctx) {
+    if (!ctx->stats_pending) return PTB_OK;
+    ptb_ctx *m = const_cast<ptb_ctx *>(ctx);
+    CU(m, cudaSetDevice(ctx->device));
+    CU(m, cudaStreamSynchronize(ctx->pending_stream));
+    float ms = 0.f;
+    CU(m, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    unsigned long long cnt[4] = {0, 0, 0, 0};
+    CU(m, cudaMemcpy(cnt, ctx->seg_counter.p, sizeof cnt, cudaMemcpyDeviceToHost));
+    m->stats.render_ms = ms;
+    m->stats.segments = cnt[0];
+    m->stats.bvh_nodes_visited = cnt[1];
+    m->stats.bvh_prims_tested = cnt[2];
+    ctx->stats_pending = false;
     return PTB_OK;
 }
 
 extern "C" int ptb_get_stats(const ptb_ctx *ctx, ptb_stats *out) {
     if (!ctx || !out) return PTB_ERR_ARG;
-    if (ctx->stats_pending) {
-        ptb_ctx *m = const_cast<ptb_ctx *>(ctx);
-        CU(m, cudaSetDevice(ctx->device));
-        CU(m, cudaStreamSynchronize(ctx->pending_stream));
-        float ms = 0.f;
-        CU(m, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-        unsigned long long cnt[4] = {0, 0, 0, 0};
-        CU(m, cudaMemcpy(cnt, ctx->seg_counter.p, sizeof cnt, cudaMemcpyDeviceToHost));
-        m->stats.render_ms = ms;
-        m->stats.segments = cnt[0];
-        m->stats.bvh_nodes_visited = cnt[1];
-        m->stats.bvh_prims_tested = cnt[2];
-        ctx->stats_pending = false;
-    }
+    int rc = finish_pending_stats(ctx);
+    if (rc != PTB_OK) return rc;
     *out = ctx->stats;
+    // a multi-GPU context reports the whole job: work summed over its devices, render_ms of the slowest one
+    for (const ptb_ctx *m : ctx->members) {
+        if ((rc = finish_pending_stats(m)) != PTB_OK) return rc;
+        out->segments += m->stats.segments;
+        out->samples += m->stats.samples;
+        out->kernel_launches += m->stats.kernel_launches;
+        out->bvh_nodes_visited += m->stats.bvh_nodes_visited;
+        out->bvh_prims_tested += m->stats.bvh_prims_tested;
+        out->render_ms = std::max(out->render_ms, m->stats.render_ms);
+    }
     return PTB_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
 // render
 // ------------------------------------------------------------------------------------------------
-static int render_device_impl(ptb_ctx *ctx, int width, int height, uint64_t spp_begin, uint64_t spp_count, uint64_t seed,
-                              float *d_sum_rgb, void *cuda_stream, const volatile int32_t *cancel, volatile uint64_t *samples_done,
-                              bool fresh_frame);
+namespace {
 
-extern "C" int ptb_render_device(ptb_ctx *ctx, int width, int height, uint64_t spp_begin, uint64_t spp_count, uint64_t seed,
-                                 float *d_sum_rgb, void *cuda_stream, const volatile int32_t *cancel,
-                                 volatile uint64_t *samples_done) {
-    return render_device_impl(ctx, width, height, spp_begin, spp_count, seed, d_sum_rgb, cuda_stream, cancel, samples_done, false);
+struct Preview {  // progressive previews (RenderUpdate.image, mod.rs:965-982): resolved partial mean handed to a callback
+    ptb_preview_fn fn = nullptr;
+    void *user = nullptr;
+    double interval_ms = 500.0;
+};
+
+#ifdef PTB_CHECK
+// turns a bounds violation recorded by a kernel into an error (the stream must be idle)
+int check_word_result(ptb_ctx *ctx) {
+    int word = 0;
+    CU(ctx, cudaMemcpy(&word, ctx->check_word.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (word != 0) {
+        cudaMemset(ctx->check_word.p, 0, sizeof(int));
+        return fail(ctx, PTB_ERR_STATE, "PTB_CHECK: a kernel saw an out-of-bounds index, code " + std::to_string(word) +
+                                            " (1 stack, 2 queue, 3 slot, 4 trace list, 5 ray, 6 stream, 7 node, 8 primitive)");
+    }
+    return PTB_OK;
 }
+#endif
 
 // fresh_frame: the buffer's content is undefined and counts as zero; the first batch overwrites it instead of accumulating
-static int render_device_impl(ptb_ctx *ctx, int width, int height, uint64_t spp_begin, uint64_t spp_count, uint64_t seed,
-                              float *d_sum_rgb, void *cuda_stream, const volatile int32_t *cancel, volatile uint64_t *samples_done,
-                              bool fresh_frame) {
+int render_device_impl(ptb_ctx *ctx, int width, int height, uint64_t spp_begin, uint64_t spp_count, uint64_t seed, float *d_sum_rgb,
+                       void *cuda_stream, const volatile int32_t *cancel, volatile uint64_t *samples_done, bool fresh_frame,
+                       const Preview *preview = nullptr) {
     if (!ctx) return fail(nullptr, PTB_ERR_ARG, "ptb_render_device: ctx is null");
     if (!ctx->has_scene) return fail(ctx, PTB_ERR_STATE, "ptb_render_device: no scene uploaded");
     if (width <= 0 || height <= 0 || !d_sum_rgb) return fail(ctx, PTB_ERR_ARG, "ptb_render_device: bad argument");
@@ -540,7 +611,8 @@ static int render_device_impl(ptb_ctx *ctx, int width, int height, uint64_t spp_
     if (spp_begin + spp_count < spp_begin) return fail(ctx, PTB_ERR_ARG, "ptb_render_device: sample range overflows");
     CU(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);  // NULL = the legacy default stream, as in CUDA
-    const bool interactive = cancel != nullptr || samples_done != nullptr;
+    const bool with_preview = preview && preview->fn;
+    const bool interactive = cancel != nullptr || samples_done != nullptr || with_preview;
 
     RenderArgs a{};
     a.width = width; a.height = height; a.seed = seed; a.sum_rgb = d_sum_rgb;
@@ -555,22 +627,29 @@ static int render_device_impl(ptb_ctx *ctx, int width, int height, uint64_t spp_
     CU(ctx, cudaMemsetAsync(ctx->seg_counter.p, 0, 4 * sizeof(unsigned long long), st));
     CU(ctx, cudaEventRecord(ctx->ev0, st));
     const uint64_t npix = static_cast<uint64_t>(width) * static_cast<uint64_t>(height);
-    // batch size: bounded work per launch so cancel / progress stay responsive (samples per launch ~ 2^31)
-    uint64_t batch = std::max<uint64_t>(1, (1ull << 31) / npix);
+    // auto: the wavefront integrator when the scene has a BVH, and also for images too small to give every resident
+    // megakernel warp two pixel tiles (measured: cornell 450x300 974 vs 800 Mpaths/s; at 1920x1080 the megakernel wins)
+    const bool has_bvh = ctx->ds.bvh_root != BVH_EMPTY_REF;
+    const bool small_image = a.n_tiles < 2 * ctx->sm_count * (RENDER_MIN_BLOCKS * RENDER_THREADS / 32);
+    const bool wavefront = ctx->integrator == 2 || (ctx->integrator == 0 && (has_bvh || small_image));
+    // Work per launch.  The cancel flag is polled and progress published between launches only (the reference polls per pixel,
+    // mod.rs:1003), so a caller that watches either gets launches of roughly 0.1-0.2 s: 2^28 samples on shared-memory scenes
+    // (~2 Gpaths/s), 2^25 through a BVH; otherwise 2^31 samples per launch keep the launch count low.
+    const uint64_t per_launch = !interactive ? (1ull << 31) : (has_bvh ? (1ull << 25) : (1ull << 28));
+    uint64_t batch = std::max<uint64_t>(1, per_launch / npix);
+    if (wavefront)  // whole wavefront batches: a launch smaller than the paths in flight would leave the queues short
+        batch = std::max<uint64_t>(batch, std::max<uint64_t>(1, ctx->wf_opt.target_paths / npix));
     uint64_t done = 0;
     int rc = PTB_OK;
+    double last_preview = now_ms();
     while (done < spp_count) {
         if (cancel && *cancel) { rc = PTB_CANCELLED; break; }
         const uint64_t n = std::min(batch, spp_count - done);
         a.spp_begin = spp_begin + done;
         a.spp_count = n;
         a.fb_zero = (fresh_frame && done == 0) ? 1 : 0;
-        // auto: the wavefront integrator when the scene has a BVH, and also for images too small to give every resident
-        // megakernel warp two pixel tiles (measured: cornell 450x300 974 vs 800 Mpaths/s; at 1920x1080 the megakernel wins)
-        const bool small_image = a.n_tiles < 2 * ctx->sm_count * (RENDER_MIN_BLOCKS * RENDER_THREADS / 32);
-        const bool wavefront = ctx->integrator == 2 || (ctx->integrator == 0 && (ctx->ds.bvh_root != BVH_EMPTY_REF || small_image));
         if (wavefront) {
-            CU(ctx, wavefront_render(ctx->ds, a, ctx->wf, ctx->sm_count, (size_t)ctx->wavefront_paths, ctx->wf_refill, ctx->wf_descend_min, ctx->wf_coop, ctx->wf_sort, st, &ctx->stats.kernel_launches));
+            CU(ctx, wavefront_render(ctx->ds, a, ctx->wf, ctx->sm_count, ctx->wf_opt, st, &ctx->stats.kernel_launches));
         } else {
             CU(ctx, cudaMemsetAsync(ctx->tile_counter.p, 0, sizeof(int), st));
             CU(ctx, launch_render(ctx->ds, a, ctx->sm_count, st));
@@ -580,28 +659,177 @@ static int render_device_impl(ptb_ctx *ctx, int width, int height, uint64_t spp_
         if (interactive) {
             CU(ctx, cudaStreamSynchronize(st));
             if (samples_done) *samples_done = done * npix;
+            if (with_preview && done < spp_count && now_ms() - last_preview >= preview->interval_ms) {
+                // RenderUpdate.image: the mean of the samples finished so far, clamped like the final image (mod.rs:849-856)
+                const size_t nfl = npix * 3;
+                CU(ctx, ctx->preview.resize(nfl));
+                if (ctx->preview_host_floats < nfl) {
+                    if (ctx->preview_host) cudaFreeHost(ctx->preview_host);
+                    ctx->preview_host = nullptr; ctx->preview_host_floats = 0;
+                    CU(ctx, cudaMallocHost(reinterpret_cast<void **>(&ctx->preview_host), nfl * sizeof(float)));
+                    ctx->preview_host_floats = nfl;
+                }
+                CU(ctx, launch_resolve(d_sum_rgb, nfl, done, ctx->preview.p, ctx->sm_count, st));
+                CU(ctx, cudaMemcpyAsync(ctx->preview_host, ctx->preview.p, nfl * sizeof(float), cudaMemcpyDeviceToHost, st));
+                CU(ctx, cudaStreamSynchronize(st));
+                ctx->stats.kernel_launches++;
+                preview->fn(preview->user, ctx->preview_host, width, height, done, spp_count);
+                last_preview = now_ms();
+            }
         }
     }
     if (fresh_frame && done == 0)  // nothing was rendered (no samples asked for, or cancelled at once): the frame is black
         CU(ctx, cudaMemsetAsync(d_sum_rgb, 0, npix * 3 * sizeof(float), st));
     CU(ctx, cudaEventRecord(ctx->ev1, st));
     ctx->stats.samples = done * npix;
+    ctx->stats_pending = true;
+    ctx->pending_stream = st;
     if (interactive) {
-        CU(ctx, cudaStreamSynchronize(st));
-        float ms = 0.f;
-        CU(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-        ctx->stats.render_ms = ms;
-        unsigned long long cnt[4] = {0, 0, 0, 0};
-        CU(ctx, cudaMemcpy(cnt, ctx->seg_counter.p, sizeof cnt, cudaMemcpyDeviceToHost));
-        ctx->stats.segments = cnt[0];
-        ctx->stats.bvh_nodes_visited = cnt[1];
-        ctx->stats.bvh_prims_tested = cnt[2];
-        ctx->stats_pending = false;
-    } else {
-        ctx->stats_pending = true;
-        ctx->pending_stream = st;
+        const int frc = finish_pending_stats(ctx);
+        if (frc != PTB_OK) return frc;
     }
+#ifdef PTB_CHECK
+    CU(ctx, cudaStreamSynchronize(st));
+    if (const int crc = check_word_result(ctx)) return crc;
+#endif
     return rc;
+}
+
+// one frame on one context: render into ctx->fb, resolve, copy to the host
+int render_one(ptb_ctx *ctx, int width, int height, uint64_t spp_begin, uint64_t spp_count, uint64_t seed, int out_kind, float *out_rgb,
+               const volatile int32_t *cancel, volatile uint64_t *samples_done, const Preview *preview) {
+    CU(ctx, cudaSetDevice(ctx->device));
+    const size_t nfl = static_cast<size_t>(width) * static_cast<size_t>(height) * 3;
+    CU(ctx, ctx->fb.resize(nfl));
+    // (no progress pointer is invented here: a caller that passes neither cancel nor samples_done gets no per-launch sync)
+    int rc = render_device_impl(ctx, width, height, spp_begin, spp_count, seed, ctx->fb.p, ctx->stream, cancel, samples_done,
+                                /*fresh_frame=*/true, preview);
+    if (rc < 0) return rc;
+    const uint64_t spp_done = ctx->stats.samples / (static_cast<uint64_t>(width) * static_cast<uint64_t>(height));
+    if (out_kind == PTB_OUT_MEAN && spp_done > 0) {
+        CU(ctx, launch_resolve(ctx->fb.p, nfl, rc == PTB_CANCELLED ? spp_done : spp_count, ctx->fb.p, ctx->sm_count, ctx->stream));
+        ctx->stats.kernel_launches++;
+    }
+    CU(ctx, cudaMemcpyAsync(out_rgb, ctx->fb.p, nfl * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return rc;
+}
+
+// One frame on a multi-GPU context: device g renders the global sample indices [g*spp/G, (g+1)*spp/G) of every pixel
+// into its own unclamped sum framebuffer, one host thread per device; then every device reduces ITS slice of the image straight
+// out of the peers' framebuffers over NVLink (k_peer_reduce_resolve: fixed rank order ((fb0+fb1)+fb2)+..., so the image is
+// deterministic), resolves it and stores it into device 0's buffer, which is copied to the host.
+int render_multi(ptb_ctx *ctx, int width, int height, uint64_t spp_begin, uint64_t spp_count, uint64_t seed, int out_kind, float *out_rgb,
+                 const volatile int32_t *cancel, volatile uint64_t *samples_done, const Preview *preview) {
+    const size_t G = ctx->members.size() + 1;
+    const uint64_t npix = static_cast<uint64_t>(width) * static_cast<uint64_t>(height);
+    const size_t nfl = npix * 3;
+    std::vector<ptb_ctx *> dev(G);
+    dev[0] = ctx;
+    for (size_t g = 1; g < G; ++g) dev[g] = ctx->members[g - 1];
+    for (ptb_ctx *m : dev)
+        if (!m->has_scene) return fail(ctx, PTB_ERR_STATE, "ptb_render: no scene uploaded");
+    std::unique_ptr<volatile uint64_t[]> progress(new volatile uint64_t[G]);
+    for (size_t g = 0; g < G; ++g) progress[g] = 0;
+    std::vector<int> rc(G, PTB_OK);
+    std::atomic<size_t> running{G};
+    const bool watch = cancel != nullptr || samples_done != nullptr || (preview && preview->fn);
+    std::vector<std::thread> th;
+    for (size_t g = 0; g < G; ++g)
+        th.emplace_back([&, g] {
+            ptb_ctx *m = dev[g];
+            const uint64_t b = spp_count * g / G, e = spp_count * (g + 1) / G;  // the split of distributed.py: shard_samples
+            cudaError_t ce = cudaSetDevice(m->device);
+            if (ce == cudaSuccess) ce = m->fb.resize(nfl);
+            if (ce != cudaSuccess) rc[g] = cuda_fail(m, ce, "ptb_render (multi): framebuffer");
+            else {
+                // previews come from device 0's share alone: an unbiased partial mean of the same image
+                rc[g] = render_device_impl(m, width, height, spp_begin + b, e - b, seed, m->fb.p, m->stream, cancel,
+                                           watch ? &progress[g] : nullptr, /*fresh_frame=*/true, g == 0 ? preview : nullptr);
+                if (rc[g] >= 0 && cudaStreamSynchronize(m->stream) != cudaSuccess) rc[g] = fail(m, PTB_ERR_CUDA, "ptb_render (multi): sync");
+            }
+            running.fetch_sub(1);
+        });
+    while (running.load() > 0) {  // the calling thread publishes the job's progress (processed_pixel_count analogue, mod.rs:850)
+        if (samples_done) {
+            uint64_t sum = 0;
+            for (size_t g = 0; g < G; ++g) sum += progress[g];
+            *samples_done = sum;
+        }
+        std::this_thread::sleep_for(std::chrono::milliseconds(watch ? 5 : 1));
+    }
+    for (auto &t : th) t.join();
+    int result = PTB_OK;
+    uint64_t samples = 0;
+    for (size_t g = 0; g < G; ++g) {
+        if (rc[g] < 0) {
+            ctx->err = "device " + std::to_string(dev[g]->device) + ": " + dev[g]->err;
+            g_thread_error = ctx->err;
+            return rc[g];
+        }
+        if (rc[g] == PTB_CANCELLED) result = PTB_CANCELLED;
+        samples += dev[g]->stats.samples;
+    }
+    if (samples_done) *samples_done = samples;
+    const uint64_t spp_done = samples / npix;  // (a cancelled frame: every device stopped after whole launches)
+    const bool resolve = out_kind == PTB_OUT_MEAN && spp_done > 0;
+    const uint64_t divisor = resolve ? (result == PTB_CANCELLED ? spp_done : spp_count) : 0;  // 0 = raw sum
+    PeerPtrs pp{};
+    if (ctx->peer_access) {
+        for (size_t g = 0; g < G; ++g) pp.p[g] = dev[g]->fb.p;
+        for (size_t g = 0; g < G; ++g) {  // slice g of the image is reduced by device g, written into device 0's buffer (P2P store)
+            const uint64_t f0 = (nfl * g / G) & ~3ull, f1 = g + 1 == G ? nfl : ((nfl * (g + 1) / G) & ~3ull);
+            CU(ctx, cudaSetDevice(dev[g]->device));
+            CU(ctx, launch_peer_reduce_resolve(pp, (int)G, f0, f1 - f0, divisor, ctx->fb.p, dev[g]->sm_count, dev[g]->stream));
+            dev[g]->stats.kernel_launches++;
+        }
+        for (size_t g = 0; g < G; ++g) {
+            CU(ctx, cudaSetDevice(dev[g]->device));
+            CU(ctx, cudaStreamSynchronize(dev[g]->stream));
+        }
+        CU(ctx, cudaSetDevice(ctx->device));
+    } else {  // no peer access between these devices: stage the members' framebuffers on device 0 and reduce there
+        CU(ctx, cudaSetDevice(ctx->device));
+        if (ctx->peer_stage.size() < G - 1 || ctx->peer_stage_floats < nfl) {
+            for (float *p : ctx->peer_stage) cudaFree(p);
+            ctx->peer_stage.assign(G - 1, nullptr);
+            ctx->peer_stage_floats = 0;
+            for (size_t g = 1; g < G; ++g) CU(ctx, cudaMalloc(reinterpret_cast<void **>(&ctx->peer_stage[g - 1]), nfl * sizeof(float)));
+            ctx->peer_stage_floats = nfl;
+        }
+        pp.p[0] = ctx->fb.p;
+        for (size_t g = 1; g < G; ++g) {
+            CU(ctx, cudaMemcpyPeerAsync(ctx->peer_stage[g - 1], ctx->device, dev[g]->fb.p, dev[g]->device, nfl * sizeof(float), ctx->stream));
+            pp.p[g] = ctx->peer_stage[g - 1];
+        }
+        CU(ctx, launch_peer_reduce_resolve(pp, (int)G, 0, nfl, divisor, ctx->fb.p, ctx->sm_count, ctx->stream));
+        ctx->stats.kernel_launches++;
+    }
+    CU(ctx, cudaMemcpyAsync(out_rgb, ctx->fb.p, nfl * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return result;
+}
+
+int render_any(ptb_ctx *ctx, int width, int height, uint64_t spp_begin, uint64_t spp_count, uint64_t seed, int out_kind, float *out_rgb,
+               const volatile int32_t *cancel, volatile uint64_t *samples_done, const Preview *preview, const char *who) {
+    if (!ctx) return fail(nullptr, PTB_ERR_ARG, std::string(who) + ": ctx is null");
+    if (!out_rgb || width <= 0 || height <= 0) return fail(ctx, PTB_ERR_ARG, std::string(who) + ": bad argument");
+    if (out_kind != PTB_OUT_MEAN && out_kind != PTB_OUT_SUM) return fail(ctx, PTB_ERR_ARG, std::string(who) + ": bad out_kind");
+    if (out_kind == PTB_OUT_MEAN && spp_count == 0) return fail(ctx, PTB_ERR_ARG, std::string(who) + ": spp_count is 0");
+    if (!ctx->has_scene) return fail(ctx, PTB_ERR_STATE, std::string(who) + ": no scene uploaded");
+    if (spp_begin + spp_count < spp_begin) return fail(ctx, PTB_ERR_ARG, std::string(who) + ": sample range overflows");
+    if (ctx->members.empty()) return render_one(ctx, width, height, spp_begin, spp_count, seed, out_kind, out_rgb, cancel, samples_done, preview);
+    return render_multi(ctx, width, height, spp_begin, spp_count, seed, out_kind, out_rgb, cancel, samples_done, preview);
+}
+
+}  // namespace
+
+extern "C" int ptb_render_device(ptb_ctx *ctx, int width, int height, uint64_t spp_begin, uint64_t spp_count, uint64_t seed,
+                                 float *d_sum_rgb, void *cuda_stream, const volatile int32_t *cancel,
+                                 volatile uint64_t *samples_done) {
+    if (ctx && !ctx->members.empty())
+        return fail(ctx, PTB_ERR_STATE, "ptb_render_device: a multi-GPU context renders through ptb_render / ptb_render_progressive");
+    return render_device_impl(ctx, width, height, spp_begin, spp_count, seed, d_sum_rgb, cuda_stream, cancel, samples_done, false);
 }
 
 extern "C" int ptb_resolve_device(ptb_ctx *ctx, const float *d_sum_rgb, uint64_t n_floats, uint64_t spp_total, float *d_mean_rgb,
@@ -615,24 +843,63 @@ extern "C" int ptb_resolve_device(ptb_ctx *ctx, const float *d_sum_rgb, uint64_t
 
 extern "C" int ptb_render(ptb_ctx *ctx, int width, int height, uint64_t spp_begin, uint64_t spp_count, uint64_t seed, int out_kind,
                           float *out_rgb, const volatile int32_t *cancel, volatile uint64_t *samples_done) {
-    if (!ctx) return fail(nullptr, PTB_ERR_ARG, "ptb_render: ctx is null");
-    if (!out_rgb || width <= 0 || height <= 0) return fail(ctx, PTB_ERR_ARG, "ptb_render: bad argument");
-    if (out_kind != PTB_OUT_MEAN && out_kind != PTB_OUT_SUM) return fail(ctx, PTB_ERR_ARG, "ptb_render: bad out_kind");
-    if (out_kind == PTB_OUT_MEAN && spp_count == 0) return fail(ctx, PTB_ERR_ARG, "ptb_render: spp_count is 0");
-    if (!ctx->has_scene) return fail(ctx, PTB_ERR_STATE, "ptb_render: no scene uploaded");
-    CU(ctx, cudaSetDevice(ctx->device));
-    const size_t nfl = static_cast<size_t>(width) * static_cast<size_t>(height) * 3;
-    CU(ctx, ctx->fb.resize(nfl));
-    uint64_t progress = 0;
-    int rc = render_device_impl(ctx, width, height, spp_begin, spp_count, seed, ctx->fb.p, ctx->stream, cancel,
-                                samples_done ? samples_done : &progress, /*fresh_frame=*/true);
-    if (rc < 0) return rc;
-    const uint64_t spp_done = ctx->stats.samples / (static_cast<uint64_t>(width) * static_cast<uint64_t>(height));
-    if (out_kind == PTB_OUT_MEAN && spp_done > 0)
-        CU(ctx, launch_resolve(ctx->fb.p, nfl, rc == PTB_CANCELLED ? spp_done : spp_count, ctx->fb.p, ctx->sm_count, ctx->stream));
-    CU(ctx, cudaMemcpyAsync(out_rgb, ctx->fb.p, nfl * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
-    return rc;
+    return render_any(ctx, width, height, spp_begin, spp_count, seed, out_kind, out_rgb, cancel, samples_done, nullptr, "ptb_render");
+}
+
+extern "C" int ptb_render_progressive(ptb_ctx *ctx, int width, int height, uint64_t spp_begin, uint64_t spp_count, uint64_t seed,
+                                      int out_kind, float *out_rgb, const volatile int32_t *cancel, volatile uint64_t *samples_done,
+                                      double preview_interval_ms, ptb_preview_fn on_preview, void *user) {
+    Preview pv;
+    pv.fn = on_preview; pv.user = user; pv.interval_ms = preview_interval_ms > 0.0 ? preview_interval_ms : 0.0;
+    return render_any(ctx, width, height, spp_begin, spp_count, seed, out_kind, out_rgb, cancel, samples_done, &pv,
+                      "ptb_render_progressive");
+}
+
+extern "C" int ptb_create_multi(const int *device_ids, int n_devices, ptb_ctx **out) {
+    if (!out) return fail(nullptr, PTB_ERR_ARG, "ptb_create_multi: out is null");
+    *out = nullptr;
+    if (!device_ids || n_devices < 1 || n_devices > MAX_PEERS) return fail(nullptr, PTB_ERR_ARG, "ptb_create_multi: 1..16 devices");
+    for (int i = 0; i < n_devices; ++i)
+        for (int j = 0; j < i; ++j)
+            if (device_ids[i] == device_ids[j]) return fail(nullptr, PTB_ERR_ARG, "ptb_create_multi: a device is listed twice");
+    ptb_ctx *ctx = nullptr;
+    int rc = ptb_create(device_ids[0], &ctx);
+    if (rc != PTB_OK) return rc;
+    for (int i = 1; i < n_devices; ++i) {
+        ptb_ctx *m = nullptr;
+        if ((rc = ptb_create(device_ids[i], &m)) != PTB_OK) { ptb_destroy(ctx); return rc; }
+        ctx->members.push_back(m);
+    }
+    // peer access between every pair: the reduce kernel of device g loads from all framebuffers and stores into device 0's
+    bool all = n_devices > 1;
+    for (int i = 0; i < n_devices && all; ++i)
+        for (int j = 0; j < n_devices && all; ++j) {
+            if (i == j) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, device_ids[i], device_ids[j]) != cudaSuccess || !can) all = false;
+        }
+    if (all)
+        for (int i = 0; i < n_devices; ++i) {
+            cudaSetDevice(device_ids[i]);
+            for (int j = 0; j < n_devices; ++j) {
+                if (i == j) continue;
+                const cudaError_t e = cudaDeviceEnablePeerAccess(device_ids[j], 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) all = false;
+                cudaGetLastError();
+            }
+        }
+    ctx->peer_access = all;
+    cudaSetDevice(device_ids[0]);
+    *out = ctx;
+    return PTB_OK;
+}
+
+extern "C" int ptb_device_ids(const ptb_ctx *ctx, int *ids, int cap) {
+    if (!ctx) return 0;
+    const int n = 1 + (int)ctx->members.size();
+    if (ids)
+        for (int g = 0; g < n && g < cap; ++g) ids[g] = g == 0 ? ctx->device : ctx->members[g - 1]->device;
+    return n;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -25,11 +25,13 @@ namespace ptb {
 
 constexpr int BVH_STACK = 96;
 constexpr int BVH_EMPTY_REF = (int)0x80000000;
+constexpr int BVH_TOP_BIT = 1 << 30;  // inner-node ref that indexes DScene::bvh_top (the copy of the top levels) instead of bvh_nodes
+constexpr int BVH_TOP_MAX = 341;      // nodes of five complete four-wide levels
 
 __device__ __forceinline__ float safe_rcp_dir(float d) {
     // a zero (or denormal) direction component would give inf * 0 = NaN in the slab test; 1e-20 keeps it finite
     const float a = fabsf(d) < 1e-20f ? copysignf(1e-20f, d) : d;
-    return __frcp_rn(a);
+    return rcp_rn_normal(a);  // |a| in [1e-20, 1]: the normal range, where this is __frcp_rn bit for bit (ptb_selftest)
 }
 
 // returns entry distance of the padded box, or a negative number if [0, tmax] misses it
@@ -55,29 +57,31 @@ __device__ __forceinline__ void cswap(float &ta, int &ra, float &tb, int &rb) {
     const int r = s ? rb : ra; rb = s ? ra : rb; ra = r;
 }
 
-// The traversal stack holds (child ref, entry distance) pairs.  PTB_STK(i) names entry i; the includer may define it
-// before including this header's macros (the wavefront trace kernel keeps the first entries in shared memory).
+// The traversal stack holds (child ref, entry distance) pairs.  PTB_STK_LD(i) reads entry i, PTB_STK_ST(i, v) writes it; the
+// includer defines both before using the macros below (the wavefront trace kernel keeps the first entries in shared memory
+// and addresses the two memories explicitly: a pointer select would turn every access into a generic LD/ST).
 #define PTB_BVH_POP()                                                    \
     do {                                                                 \
         cur = BVH_EMPTY_REF;                                             \
         while (sp > 0) {                                                 \
             --sp;                                                        \
-            const int2 e_ = PTB_STK(sp);                                 \
+            const int2 e_ = PTB_STK_LD(sp);                              \
             if (__int_as_float(e_.y) <= best.t) { cur = e_.x; break; }   \
         }                                                                \
     } while (0)
 #define PTB_BVH_PUSH(ref_, t_)                                           \
     do {                                                                 \
-        PTB_STK(sp) = make_int2((ref_), __float_as_int(t_));             \
-        sp++;                                                            \
+        if (PTB_CHECKED(sp < BVH_STACK, PTB_CHK_STACK, sc.check)) {      \
+            PTB_STK_ST(sp, make_int2((ref_), __float_as_int(t_)));       \
+            sp++;                                                        \
+        }                                                                \
     } while (0)
 
 // One step through a four-wide inner node: test the four child boxes, continue with the nearest one that is hit and
 // postpone the others (far to near, so the nearer is popped first) together with their entry distances.
-#define PTB_BVH_NODE_STEP()                                                                                      \
+// PTB_BVH_NODE_TEST expects the node in a01_, a23_, b01_, b23_ (children 0|1, 2|3: lo.xyz hi.x, then hi.yz ref -).
+#define PTB_BVH_NODE_TEST()                                                                                      \
     do {                                                                                                         \
-        const float4 *nd_ = sc.bvh_nodes + 8 * (size_t)cur;                                                      \
-        const F8 a01_ = ld256(nd_), a23_ = ld256(nd_ + 2), b01_ = ld256(nd_ + 4), b23_ = ld256(nd_ + 6);         \
         float t0_ = slab_t(a01_.a.x, a01_.a.y, a01_.a.z, a01_.a.w, b01_.a.x, b01_.a.y, id, ood, best.t);         \
         float t1_ = slab_t(a01_.b.x, a01_.b.y, a01_.b.z, a01_.b.w, b01_.b.x, b01_.b.y, id, ood, best.t);         \
         float t2_ = slab_t(a23_.a.x, a23_.a.y, a23_.a.z, a23_.a.w, b23_.a.x, b23_.a.y, id, ood, best.t);         \
@@ -96,12 +100,20 @@ __device__ __forceinline__ void cswap(float &ta, int &ra, float &tb, int &rb) {
             if (t1_ < inf_) PTB_BVH_PUSH(r1_, t1_);                                                              \
         } else PTB_BVH_POP();                                                                                    \
     } while (0)
+#define PTB_BVH_NODE_STEP()                                                                                      \
+    do {                                                                                                         \
+        const float4 *nd_ = sc.bvh_nodes + 8 * (size_t)cur;                                                      \
+        (void)PTB_CHECKED(cur < sc.n_bvh_nodes, PTB_CHK_NODE, sc.check);                                             \
+        const F8 a01_ = ld256(nd_), a23_ = ld256(nd_ + 2), b01_ = ld256(nd_ + 4), b23_ = ld256(nd_ + 6);         \
+        PTB_BVH_NODE_TEST();                                                                                     \
+    } while (0)
 
 // Tests the primitives of the leaf `cur` (reference arithmetic, prio tie-break, lazy mesh gate), then pops.
 #define PTB_BVH_LEAF()                                                                                           \
     do {                                                                                                         \
         const int code_ = ~cur;                                                                                  \
         const int first_ = code_ >> 3, count_ = (code_ & 7) + 1;                                                 \
+        (void)PTB_CHECKED(first_ + count_ <= sc.n_bvh_prims, PTB_CHK_PRIM, sc.check);                                \
         for (int k = first_; k < first_ + count_; ++k) {                                                         \
             const F8 ae_ = ld256(sc.bvh_tri + 2 * (size_t)k);                                                    \
             const float4 A = ae_.a, E1 = ae_.b, E2 = __ldg(&sc.bvh_e2[k]);                                      \
@@ -140,7 +152,8 @@ __device__ __forceinline__ void bvh_closest_hit(const DScene &sc, V3 o, V3 d, Hi
     const V3 id = mk3(safe_rcp_dir(d.x), safe_rcp_dir(d.y), safe_rcp_dir(d.z));
     const V3 ood = mk3(o.x * id.x, o.y * id.y, o.z * id.z);
     int2 stack_[BVH_STACK];
-#define PTB_STK(i) stack_[i]
+#define PTB_STK_LD(i) stack_[i]
+#define PTB_STK_ST(i, v) stack_[i] = (v)
     int sp = 0;
     int gate_obj = -1;
     bool gate_pass = false;
@@ -148,7 +161,8 @@ __device__ __forceinline__ void bvh_closest_hit(const DScene &sc, V3 o, V3 d, Hi
         while (cur >= 0) PTB_BVH_NODE_STEP();
         if (cur != BVH_EMPTY_REF) PTB_BVH_LEAF();
     }
-#undef PTB_STK
+#undef PTB_STK_LD
+#undef PTB_STK_ST
 }
 
 }  // namespace ptb

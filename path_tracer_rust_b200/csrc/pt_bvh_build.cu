@@ -231,6 +231,41 @@ __global__ void k_gather_prims(const float4 *__restrict__ recs, const int *__res
     }
 }
 
+// Copies the top `levels` four-wide levels (breadth first from node 0, at most `cap` nodes) into `top`; a child ref that points to
+// another copied node becomes BVH_TOP_BIT | its index in `top`.  One CTA; the order inside a level does not matter.
+__global__ void __launch_bounds__(256) k_top_levels(const float4 *__restrict__ nodes, int levels, int cap, float4 *__restrict__ top,
+                                                    int *__restrict__ n_top) {
+    __shared__ int s_src[2][256], s_dst[2][256], s_n[2], s_total;
+    if (threadIdx.x == 0) { s_src[0][0] = 0; s_dst[0][0] = 0; s_n[0] = 1; s_n[1] = 0; s_total = 1; }
+    __syncthreads();
+    for (int lvl = 0; lvl < levels; ++lvl) {
+        const int c = lvl & 1, nx = c ^ 1;
+        const int n_cur = s_n[c];
+        __syncthreads();
+        if (threadIdx.x == 0) s_n[nx] = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n_cur; i += blockDim.x) {
+            const int src = s_src[c][i], dst = s_dst[c][i];
+            float4 rec[8];
+            for (int k = 0; k < 8; ++k) rec[k] = nodes[8 * (size_t)src + k];
+            for (int k = 0; k < 4; ++k) {
+                const int ref = __float_as_int(rec[4 + k].z);
+                if (ref >= 0 && lvl + 1 < levels) {
+                    const int slot = atomicAdd(&s_total, 1);
+                    if (slot < cap) {
+                        const int j = atomicAdd(&s_n[nx], 1);  // (a level of a four-wide tree below depth 5 has at most 256 nodes)
+                        s_src[nx][j] = ref; s_dst[nx][j] = slot;
+                        rec[4 + k].z = __int_as_float(BVH_TOP_BIT | slot);
+                    } else atomicSub(&s_total, 1);  // no room: the child stays a reference into bvh_nodes
+                }
+            }
+            for (int k = 0; k < 8; ++k) top[8 * (size_t)dst + k] = rec[k];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *n_top = min(s_total, cap);
+}
+
 template <typename T>
 cudaError_t dev_alloc(T **p, size_t n) { return cudaMalloc(reinterpret_cast<void **>(p), std::max<size_t>(n, 1) * sizeof(T)); }
 
@@ -274,6 +309,8 @@ void choose_bvh_objects(const ptb_scene_desc &desc, size_t max_smem_bytes, const
 void bvh_release(BvhDevice &b) {
     if (b.nodes) cudaFree(b.nodes);
     if (b.tris) cudaFree(b.tris);
+    if (b.top) cudaFree(b.top);
+    if (b.top_count) cudaFree(b.top_count);
     b = BvhDevice{};
 }
 
@@ -289,6 +326,8 @@ cudaError_t bvh_build(const ptb_scene_desc &desc, const std::vector<char> &in_bv
     out.max_depth = 0;
     ds.bvh_root = BVH_EMPTY_REF;
     ds.bvh_nodes = nullptr; ds.bvh_tri = nullptr; ds.bvh_e2 = nullptr; ds.bvh_fin = nullptr; ds.n_bvh_nodes = 0;
+    ds.bvh_top = nullptr; ds.n_bvh_top = 0; ds.n_bvh_prims = 0;
+    ds.bvh_lo = mk3(0.f, 0.f, 0.f); ds.bvh_hi = mk3(0.f, 0.f, 0.f);
     if (build_ms) *build_ms = 0.0;
 
     // ---- host: distance bound D, primitive records, pads ----------------------------------------------------------------
@@ -371,7 +410,8 @@ cudaError_t bvh_build(const ptb_scene_desc &desc, const std::vector<char> &in_bv
     size_t tmp_bytes = 0, tmp2 = 0;
     const int T = 256, B = (n + T - 1) / T;
     const int n_inner = n - 1;
-    int h_depth = 0, n_alive = 0;
+    int h_depth = 0, n_alive = 0, n_top = 0;
+    float4 h_root[2];  // padded box around everything in the BVH
 
     BV(cudaEventCreate(&ev0)); BV(cudaEventCreate(&ev1));
     BV(dev_alloc(&d_recs, 3 * (size_t)n)); BV(dev_alloc(&d_pads, (size_t)n));
@@ -422,6 +462,8 @@ cudaError_t bvh_build(const ptb_scene_desc &desc, const std::vector<char> &in_bv
         BV(cudaMemcpyAsync(&last_alive, d_sel + (n_inner - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
         BV(cudaMemcpyAsync(&last_new, d_new + (n_inner - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
         BV(cudaMemcpyAsync(&h_depth, d_depth, sizeof(int), cudaMemcpyDeviceToHost, st));
+        BV(cudaMemcpyAsync(&h_root[0], d_nlo, sizeof(float4), cudaMemcpyDeviceToHost, st));  // Karras' node 0 is the root
+        BV(cudaMemcpyAsync(&h_root[1], d_nhi, sizeof(float4), cudaMemcpyDeviceToHost, st));
         BV(cudaStreamSynchronize(st));
         n_alive = last_alive + last_new;
         // a four-wide step pushes at most three entries per pair of binary levels
@@ -430,6 +472,9 @@ cudaError_t bvh_build(const ptb_scene_desc &desc, const std::vector<char> &in_bv
         BV(cudaMemcpyAsync(d_idx2, d_idx, 0, cudaMemcpyDeviceToDevice, st));
         int zero = 0;
         BV(cudaMemcpyAsync(d_idx2, &zero, sizeof(int), cudaMemcpyHostToDevice, st));
+        BV(cudaMemcpyAsync(&h_root[0], d_blo, sizeof(float4), cudaMemcpyDeviceToHost, st));
+        BV(cudaMemcpyAsync(&h_root[1], d_bhi, sizeof(float4), cudaMemcpyDeviceToHost, st));
+        BV(cudaStreamSynchronize(st));
     }
     if (n_alive > 0) {
         if (out.cap_nodes < (size_t)n_alive) {
@@ -442,6 +487,12 @@ cudaError_t bvh_build(const ptb_scene_desc &desc, const std::vector<char> &in_bv
                                                             d_bhi, d_nlo, d_nhi, out.nodes);
         BV(cudaGetLastError());
         ds.bvh_root = 0;  // Karras' internal node 0 is the root and is always alive here
+        if (opt.top_levels > 0) {
+            if (!out.top) { BV(dev_alloc(&out.top, 8 * (size_t)BVH_TOP_MAX)); BV(dev_alloc(&out.top_count, 1)); }
+            k_top_levels<<<1, 256, 0, st>>>(out.nodes, std::min(opt.top_levels, 5), BVH_TOP_MAX, out.top, out.top_count);
+            BV(cudaGetLastError());
+            BV(cudaMemcpyAsync(&n_top, out.top_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+        }
     } else {
         ds.bvh_root = ~((0 << 3) | (n - 1));  // the whole set fits one leaf
     }
@@ -456,12 +507,9 @@ cudaError_t bvh_build(const ptb_scene_desc &desc, const std::vector<char> &in_bv
     }
     out.n_nodes = (unsigned)n_alive; out.n_tris = n_tris; out.n_spheres = n_sph; out.max_depth = h_depth;
     ds.bvh_nodes = out.nodes; ds.bvh_tri = out.tris; ds.bvh_e2 = out.tris + 2 * (size_t)n; ds.bvh_fin = out.tris + 3 * (size_t)n;
-    ds.n_bvh_nodes = n_alive;
-    ds.world_lo = mk3((float)lo[0], (float)lo[1], (float)lo[2]);
-    {
-        auto inv = [&](int k) { const double e = hi[k] - lo[k]; return (float)(e > 0 ? 1.0 / e : 0.0); };
-        ds.world_inv = mk3(inv(0), inv(1), inv(2));
-    }
+    ds.n_bvh_nodes = n_alive; ds.n_bvh_prims = n;
+    ds.bvh_top = out.top; ds.n_bvh_top = n_top;
+    ds.bvh_lo = mk3(h_root[0].x, h_root[0].y, h_root[0].z); ds.bvh_hi = mk3(h_root[1].x, h_root[1].y, h_root[1].z);
 
 done:
     cudaFree(d_recs); cudaFree(d_pads); cudaFree(d_blo); cudaFree(d_bhi); cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_idx);

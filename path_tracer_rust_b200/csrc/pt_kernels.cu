@@ -222,6 +222,8 @@ __global__ void k_resolve(const float *__restrict__ sum, unsigned long long n, f
 
 // Multi-GPU: sum the ranks' partial framebuffers (peer memory, NVLink loads), resolve, store (possibly into a peer's buffer).
 // The order of the adds is the rank order, whatever the interconnect does: ((fb0 + fb1) + fb2) + ...
+// spp = 0: store the raw sum (PTB_OUT_SUM of a multi-GPU context) instead of the clamped mean.
+__device__ __forceinline__ float resolve1(float s, float spp) { return spp > 0.0f ? fminf(fmaxf(PTB_DIV(s, spp), 0.0f), 1.0f) : s; }
 __global__ void __launch_bounds__(256) k_peer_reduce_resolve(const PeerPtrs peers, int n_peers, unsigned long long first,
                                                              unsigned long long n, float spp, float *__restrict__ dst) {
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
@@ -236,20 +238,19 @@ __global__ void __launch_bounds__(256) k_peer_reduce_resolve(const PeerPtrs peer
                 s.x = s.x + v.x; s.y = s.y + v.y; s.z = s.z + v.z; s.w = s.w + v.w;
             }
             float4 r;
-            r.x = fminf(fmaxf(PTB_DIV(s.x, spp), 0.0f), 1.0f); r.y = fminf(fmaxf(PTB_DIV(s.y, spp), 0.0f), 1.0f);
-            r.z = fminf(fmaxf(PTB_DIV(s.z, spp), 0.0f), 1.0f); r.w = fminf(fmaxf(PTB_DIV(s.w, spp), 0.0f), 1.0f);
+            r.x = resolve1(s.x, spp); r.y = resolve1(s.y, spp); r.z = resolve1(s.z, spp); r.w = resolve1(s.w, spp);
             reinterpret_cast<float4 *>(dst)[at] = r;
         }
         for (unsigned long long i = n4 * 4 + tid; i < n; i += stride) {
             float s = peers.p[0][first + i];
             for (int g = 1; g < n_peers; ++g) s = s + peers.p[g][first + i];
-            dst[first + i] = fminf(fmaxf(PTB_DIV(s, spp), 0.0f), 1.0f);
+            dst[first + i] = resolve1(s, spp);
         }
     } else {
         for (unsigned long long i = tid; i < n; i += stride) {
             float s = peers.p[0][first + i];
             for (int g = 1; g < n_peers; ++g) s = s + peers.p[g][first + i];
-            dst[first + i] = fminf(fmaxf(PTB_DIV(s, spp), 0.0f), 1.0f);
+            dst[first + i] = resolve1(s, spp);
         }
     }
 }

@@ -1,21 +1,28 @@
-// pt_wavefront.cu -- wavefront integrator for BVH scenes (big meshes / many spheres).
+// pt_wavefront.cu -- wavefront integrator for BVH scenes (big meshes / many spheres) and for frames too small to fill the
+// megakernel's persistent warps.
 //
 // Same semantics as the megakernel (pt_kernels.cu) and as the oracle's forward twin: identical Philox events, identical
 // arithmetic, identical per-pixel summation order, hence a bit-identical framebuffer.  What changes is the schedule.
 // In a megakernel every lane walks its own BVH path and the warp runs at the pace of its slowest lane (measured: 6.5 of
 // 32 lanes active).  Here a batch of K samples of every pixel is in flight as a queue of ray segments in HBM and each
 // bounce is two kernels:
-//   k_wf_trace  persistent warps; a lane whose traversal ends writes its hit and is refilled with the next ray of the queue
-//               as soon as REFILL lanes of the warp are idle (Aila & Laine 2009), so traversal runs with mostly full warps;
-//   k_wf_shade  one thread per segment: Philox block, hit point / normal, material arm (shade_hit), appends the continuation
-//               (and the transmitted child of a deterministic refraction split) to the next queue with one warp-aggregated
-//               atomic; a finished branch stores its emission sum in its slot.
+//   k_wf_trace  persistent warps; a lane whose traversal ends writes its hit and is refilled with the next ray of the trace
+//               list as soon as `refill` lanes of the warp are idle (Aila & Laine 2009), so traversal runs with mostly full warps;
+//   k_wf_shade  one thread per segment: Philox block, hit point / normal, material arm (shade_hit), closest hit of the NEXT
+//               segment over the shared-memory list, append of the continuation (and of the transmitted child of a
+//               deterministic refraction split) to the next queue with one warp-aggregated atomic; a finished branch stores
+//               its emission sum in its slot.
+// Only segments that can reach BVH geometry are traced: generate / shade test the segment [0, t_loose] against the BVH's root
+// box (the slab test the traversal itself would start with; monotone rounding makes "misses the root box" imply "misses every
+// child box").  The queue is filled from both ends: segments to trace take indices 0, 1, 2, ... (the trace kernel reads them
+// as one dense, coalesced range), the others cap-1, cap-2, ...; one 64-bit atomic per warp advances both counts.  A scene
+// without a BVH launches no trace kernel at all.
 // Branches of a path tree are independent queue entries: event ids depend only on (branch code, depth) and every branch
 // sums its own emission, so nothing depends on the order in which they are processed.  After MAX_DEPTH bounces
-// k_wf_accumulate adds ((L0+L1)+L2)+L3 of samples s0..s0+K-1 to the pixel sum in sample order (mod.rs:846).
+// k_wf_accumulate adds ((L0+L1)+L2)+L3 of samples s0..s0+K-1 to the pixel sum in sample order (mod.rs:846); which of the
+// branches 1..3 exist is recorded per path by the split that creates them (branch_mask), so slots are neither cleared nor
+// read for branches that never existed.
 // Queue entries are 4 x float4 (o|path, d|depth+code, T, L) in SoA arrays: coalesced 16-byte loads and stores.
-#include <cub/cub.cuh>
-
 #include "pt_launch.h"
 #include "pt_scene_dev.cuh"
 #include "pt_wavefront.h"
@@ -24,57 +31,106 @@ namespace ptb {
 
 namespace {
 
-constexpr int WF_THREADS = 256;
-constexpr int WF_CHUNK = 512;  // rays a warp takes from the queue per global atomic
+constexpr int WF_CHUNK = 512;  // most rays a warp takes from the queue per global atomic
 constexpr int WF_SSTACK = 12;  // traversal-stack entries per lane kept in shared memory (deeper entries go to local memory)
 
+// closest hit of a new segment over the shared-memory list, and whether the segment can reach BVH geometry at all
 // (called by the lanes of `amask` only: they are all live)
-__device__ __forceinline__ void store_loose_hit(const WfQueue &q, size_t j, const float4 *s_obj, V3 o, V3 d, unsigned amask) {
-    Hit best;
+__device__ __forceinline__ bool loose_hit(const DScene &sc, const float4 *s_obj, V3 o, V3 d, unsigned amask, Hit &best) {
     best.t = __int_as_float(0x7f800000); best.prio = PRIO_NONE; best.ref = REF_NONE;
     closest_hit_loose(s_obj, o, d, amask, best);
-    q.hit_t[j] = best.t; q.hit_ref[j] = best.ref; q.hit_prio[j] = best.prio;
+    if (sc.bvh_root == BVH_EMPTY_REF) return true;  // (uniform) no BVH, no trace kernel: everything queues up from the front
+    const V3 id = mk3(safe_rcp_dir(d.x), safe_rcp_dir(d.y), safe_rcp_dir(d.z));
+    const V3 ood = mk3(o.x * id.x, o.y * id.y, o.z * id.z);
+    float t_in;
+    return slab(sc.bvh_lo.x, sc.bvh_lo.y, sc.bvh_lo.z, sc.bvh_hi.x, sc.bvh_hi.y, sc.bvh_hi.z, id, ood, best.t, t_in);
+}
+
+// Two-ended append, one atomic per warp (all 32 lanes call).  A lane adds up to two entries (a, b), each either to the front
+// (segments the trace kernel must see) or to the back of the queue.  ctr[0] = front count, ctr[1] = back count (one aligned
+// 64-bit word).  Returns the queue indices through ia / ib (-1: nothing to add, or the PTB_CHECK build refused it).
+__device__ __forceinline__ void append2(const DScene &sc, const WfQueue &q, int *__restrict__ ctr, bool has_a, bool front_a, bool has_b,
+                                        bool front_b, unsigned lt_mask, int &ia, int &ib) {
+    const unsigned fa = __ballot_sync(0xffffffffu, has_a && front_a), ba = __ballot_sync(0xffffffffu, has_a && !front_a);
+    const unsigned fb = __ballot_sync(0xffffffffu, has_b && front_b), bb = __ballot_sync(0xffffffffu, has_b && !front_b);
+    ia = ib = -1;
+    if ((fa | ba | fb | bb) == 0u) return;
+    const unsigned n_front = __popc(fa) + __popc(fb), n_back = __popc(ba) + __popc(bb);
+    unsigned long long old = 0;
+    if ((threadIdx.x & 31) == 0) old = atomicAdd(reinterpret_cast<unsigned long long *>(ctr), ((unsigned long long)n_back << 32) | n_front);
+    old = __shfl_sync(0xffffffffu, old, 0);
+    const int f0 = (int)(unsigned)old, b0 = (int)(unsigned)(old >> 32);
+    if (!PTB_CHECKED((long long)f0 + n_front + b0 + n_back <= (long long)q.cap, PTB_CHK_QUEUE, sc.check)) return;
+    if (has_a) ia = front_a ? f0 + __popc(fa & lt_mask) : q.cap - 1 - (b0 + __popc(ba & lt_mask));
+    if (has_b) ib = front_b ? f0 + __popc(fa) + __popc(fb & lt_mask) : q.cap - 1 - (b0 + __popc(ba) + __popc(bb & lt_mask));
 }
 
 __global__ void __launch_bounds__(256) k_wf_generate(const DScene sc, int W, int H, unsigned npix, unsigned long long s0, unsigned K,
-                                                     unsigned long long seed, WfQueue q) {
+                                                     unsigned long long seed, WfQueue q, int *__restrict__ branch_mask,
+                                                     int *__restrict__ ctr) {
     extern __shared__ float4 smem[];
     const float4 *s_obj, *s_tri;
     stage_loose(sc, smem, s_obj, s_tri);
-    const unsigned long long n = (unsigned long long)npix * K;
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const unsigned n = npix * K;  // < 2^29 (checked by the host)
+    const unsigned stride = gridDim.x * blockDim.x;
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-    const unsigned long long n_round = (n + 31ull) & ~31ull;
-    for (unsigned long long p = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; p < n_round; p += stride) {
-        const unsigned amask = __ballot_sync(0xffffffffu, p < n);
-        if (p >= n) continue;
-        const uint32_t pixel = (uint32_t)(p % npix);
-        const unsigned long long s = s0 + p / npix;
-        const int row = (int)(pixel / (uint32_t)W), px = (int)(pixel % (uint32_t)W);
-        uint32_t rnd[4];
-        philox4x32_10(pixel, (uint32_t)s, (uint32_t)(s >> 32), 0u, k0, k1, rnd);  // camera sample: event 0, slots 0,1
-        const float ysub = (float)((s / 2) % 2), xsub = (float)(s % 2);
-        const float r1 = 2.0f * u32_to_unit(rnd[0]);
-        const float r2 = 2.0f * u32_to_unit(rnd[1]);
-        V3 o, d;
-        camera_ray(sc, W, H, px, H - 1 - row, xsub, ysub, tent(r1), tent(r2), o, d);
-        q.o[p] = make_float4(o.x, o.y, o.z, __int_as_float((int)p));
-        q.d[p] = make_float4(d.x, d.y, d.z, __int_as_float(0));
-        q.T[p] = make_float4(1.f, 1.f, 1.f, 0.f);
-        q.L[p] = make_float4(0.f, 0.f, 0.f, 0.f);
-        store_loose_hit(q, p, s_obj, o, d, amask);
+    const unsigned n_round = (n + 31u) & ~31u;
+    const unsigned lt_mask = (1u << (threadIdx.x & 31)) - 1u;
+    for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < n_round; p += stride) {
+        const bool valid = p < n;
+        const unsigned amask = __ballot_sync(0xffffffffu, valid);
+        V3 o = mk3(0.f, 0.f, 0.f), d = mk3(0.f, 0.f, 1.f);
+        Hit best;
+        bool front = false;
+        if (valid) {
+            const uint32_t pixel = p % npix;
+            const unsigned long long s = s0 + p / npix;
+            const int row = (int)(pixel / (uint32_t)W), px = (int)(pixel % (uint32_t)W);
+            uint32_t rnd[4];
+            philox4x32_10(pixel, (uint32_t)s, (uint32_t)(s >> 32), 0u, k0, k1, rnd);  // camera sample: event 0, slots 0,1
+            const float ysub = (float)((s / 2) % 2), xsub = (float)(s % 2);
+            const float r1 = 2.0f * u32_to_unit(rnd[0]);
+            const float r2 = 2.0f * u32_to_unit(rnd[1]);
+            camera_ray(sc, W, H, px, H - 1 - row, xsub, ysub, tent(r1), tent(r2), o, d);
+            front = loose_hit(sc, s_obj, o, d, amask, best);
+            branch_mask[p] = 0;
+        }
+        int j, unused;
+        append2(sc, q, ctr, valid, front, false, false, lt_mask, j, unused);
+        if (j >= 0) {
+            q.o[j] = make_float4(o.x, o.y, o.z, __int_as_float((int)p));
+            q.d[j] = make_float4(d.x, d.y, d.z, __int_as_float(0));
+            q.T[j] = make_float4(1.f, 1.f, 1.f, 0.f);
+            q.L[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            q.hit_t[j] = best.t; q.hit_ref[j] = best.ref; q.hit_prio[j] = best.prio;
+        }
     }
 }
 
-// closest hit of every queued segment
-// (measured: 5 or 6 CTAs per SM with the spills that takes, or prefetching the leaf while a lane waits, are all slower or neutral)
-// `order` (optional): the queue entries in the order they should be traced (k_wf_ray_keys + radix sort); results go back to
-// the entry itself, so nothing downstream sees the order
-__global__ void __launch_bounds__(WF_THREADS, 4) k_wf_trace(const DScene sc, const WfQueue q, const int *__restrict__ n_rays_ptr,
-                                                             int *__restrict__ fetch_ptr, unsigned long long *__restrict__ counters,
-                                                             const int wf_refill, const int wf_descend_min,
-                                                             const int *__restrict__ order) {
-    const int n = *n_rays_ptr;
+// ---------------------------------------------------------------------------------------------------------------------
+// closest BVH hit of every segment on the trace list
+// (measured in round 1: 5 or 6 CTAs per SM with the spills that takes, prefetching the leaf while a lane waits, four lanes per ray
+//  and tracing in (octant, Morton cell) order are all slower or neutral: profiles/r01g, r01j; tools/experiments/)
+// Shared memory: [copy of the top levels of the BVH (sc.n_bvh_top nodes, 144-byte pitch)] [traversal stacks]
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int TOP_PITCH = 9;  // float4 per shared-memory node: 128 bytes of node + 16 bytes that spread the nodes over the banks
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_wf_trace(const DScene sc, const WfQueue q, const int *__restrict__ ctr,
+                                                                     int *__restrict__ fetch_ptr, unsigned long long *__restrict__ counters,
+                                                                     const int wf_refill, const int wf_descend_min) {
+    extern __shared__ float4 smem[];
+    float4 *const s_top = smem;
+    int2 *const s_stack = reinterpret_cast<int2 *>(smem + TOP_PITCH * sc.n_bvh_top);
+    for (int i = threadIdx.x; i < 8 * sc.n_bvh_top; i += THREADS) s_top[(i >> 3) * TOP_PITCH + (i & 7)] = __ldg(&sc.bvh_top[i]);
+    if (sc.n_bvh_top) __syncthreads();
+    const int n = ctr[0];  // the front part of the queue: the segments that can reach BVH geometry
+    // Rays are handed out in chunks (one same-address atomic per chunk instead of one per refill).  The chunk shrinks with the
+    // queue so that every warp of the grid gets about four of them: with a fixed 512 a late bounce (or a scene where few segments
+    // reach the BVH) would be traced by a handful of warps while the rest of the GPU idles (measured: 0.8-1.0 ms per launch
+    // whatever the queue length, profiles/r02c).
+    const int chunk = max(32, min(WF_CHUNK, (n / (int)(gridDim.x * (THREADS / 32) * 4)) & ~31));
+    const int root_ref = sc.n_bvh_top ? BVH_TOP_BIT : sc.bvh_root;  // top node 0 is the root's copy
     unsigned n_nodes = 0, n_prims = 0;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -89,43 +145,58 @@ __global__ void __launch_bounds__(WF_THREADS, 4) k_wf_trace(const DScene sc, con
     bool gate_pass = false;
     // traversal stack: the hot top of it lives in shared memory (entry-major, conflict-free 8-byte accesses), so a pop
     // costs a fixed ~30 cycles instead of a local-memory load that competes with node data for the L1
-    __shared__ int2 s_stack[WF_SSTACK * WF_THREADS];
     int2 l_stack[BVH_STACK - WF_SSTACK];
-#define PTB_STK(i) (*((i) < WF_SSTACK ? &s_stack[(i) * WF_THREADS + threadIdx.x] : &l_stack[(i) - WF_SSTACK]))
+#define PTB_STK_LD(i) ((i) < WF_SSTACK ? s_stack[(i) * THREADS + threadIdx.x] : l_stack[(i) - WF_SSTACK])
+#define PTB_STK_ST(i, v)                                                        \
+    do {                                                                        \
+        if ((i) < WF_SSTACK) s_stack[(i) * THREADS + threadIdx.x] = (v);        \
+        else l_stack[(i) - WF_SSTACK] = (v);                                    \
+    } while (0)
 
     for (;;) {
         const unsigned busy_mask = __ballot_sync(0xffffffffu, busy);
         const int n_idle = 32 - __popc(busy_mask);
         if (!exhausted && (n_idle >= wf_refill || busy_mask == 0u)) {
-            // the warp owns a private chunk [w_next, w_end) of the queue and only touches the global cursor when it runs dry:
-            // one same-address atomic per WF_CHUNK rays instead of one per refill
+            // the warp owns a private chunk [w_next, w_end) of the queue and only touches the global cursor when it runs dry
             if (w_next >= w_end) {
                 int base = 0;
-                if (lane == 0) base = atomicAdd(fetch_ptr, WF_CHUNK);
+                if (lane == 0) base = atomicAdd(fetch_ptr, chunk);
                 base = __shfl_sync(0xffffffffu, base, 0);
                 w_next = base;
-                w_end = min(base + WF_CHUNK, n);
+                w_end = min(base + chunk, n);
                 if (base >= n) exhausted = true;
             }
             const int idx = w_next + __popc(~busy_mask & lt_mask);
             const bool got = !busy && idx < w_end;
             w_next = min(w_next + n_idle, w_end);
             if (got) {
-                const int r = order ? __ldcs(&order[idx]) : idx;
-                const float4 qo = __ldcs(&q.o[r]), qd = __ldcs(&q.d[r]);  // streaming: keep the L2 for the BVH
-                o = mk3(qo.x, qo.y, qo.z); d = mk3(qd.x, qd.y, qd.z);
-                ray_idx = r;
-                best.t = __ldcs(&q.hit_t[r]); best.ref = __ldcs(&q.hit_ref[r]); best.prio = __ldcs(&q.hit_prio[r]);
-                id = mk3(safe_rcp_dir(d.x), safe_rcp_dir(d.y), safe_rcp_dir(d.z));
-                ood = mk3(o.x * id.x, o.y * id.y, o.z * id.z);
-                cur = sc.bvh_root; sp = 0; gate_obj = -1;
-                busy = true;
+                const int r = idx;
+                if (PTB_CHECKED(r >= 0 && r < q.cap, PTB_CHK_RAY, sc.check)) {
+                    const float4 qo = __ldcs(&q.o[r]), qd = __ldcs(&q.d[r]);  // streaming: keep the L2 for the BVH
+                    o = mk3(qo.x, qo.y, qo.z); d = mk3(qd.x, qd.y, qd.z);
+                    ray_idx = r;
+                    best.t = __ldcs(&q.hit_t[r]); best.ref = __ldcs(&q.hit_ref[r]); best.prio = __ldcs(&q.hit_prio[r]);
+                    id = mk3(safe_rcp_dir(d.x), safe_rcp_dir(d.y), safe_rcp_dir(d.z));
+                    ood = mk3(o.x * id.x, o.y * id.y, o.z * id.z);
+                    cur = root_ref; sp = 0; gate_obj = -1;
+                    busy = true;
+                }
             }
         }
         if (__ballot_sync(0xffffffffu, busy) == 0u) break;
         if (busy) {
             while (cur >= 0) {  // descend until this lane holds a leaf or is done
-                PTB_BVH_NODE_STEP();
+                F8 a01_, a23_, b01_, b23_;
+                if (cur & BVH_TOP_BIT) {  // one of the top levels: shared-memory copy
+                    const float4 *nd_ = s_top + TOP_PITCH * (cur & (BVH_TOP_BIT - 1));
+                    a01_.a = nd_[0]; a01_.b = nd_[1]; a23_.a = nd_[2]; a23_.b = nd_[3];
+                    b01_.a = nd_[4]; b01_.b = nd_[5]; b23_.a = nd_[6]; b23_.b = nd_[7];
+                } else {
+                    const float4 *nd_ = sc.bvh_nodes + 8 * (size_t)cur;
+                    (void)PTB_CHECKED(cur < sc.n_bvh_nodes, PTB_CHK_NODE, sc.check);
+                    a01_ = ld256(nd_); a23_ = ld256(nd_ + 2); b01_ = ld256(nd_ + 4); b23_ = ld256(nd_ + 6);
+                }
+                PTB_BVH_NODE_TEST();
                 n_nodes++;
                 if (__popc(__activemask()) < wf_descend_min) break;  // let the lanes that hold a leaf get on with it
             }
@@ -140,182 +211,8 @@ __global__ void __launch_bounds__(WF_THREADS, 4) k_wf_trace(const DScene sc, con
             }
         }
     }
-#undef PTB_STK
-    for (int off = 16; off > 0; off >>= 1) {
-        n_nodes += __shfl_down_sync(0xffffffffu, n_nodes, off);
-        n_prims += __shfl_down_sync(0xffffffffu, n_prims, off);
-    }
-    if (lane == 0 && (n_nodes | n_prims)) {
-        atomicAdd(&counters[1], (unsigned long long)n_nodes);
-        atomicAdd(&counters[2], (unsigned long long)n_prims);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// Cooperative trace kernel: FOUR LANES PER RAY, eight rays per warp.
-//
-// Why: with one lane per ray every diverged lane pays one L1 data-pipe wavefront per 16 bytes it loads (a 128-byte node = 8),
-// and ncu shows that pipe 90 % busy (profiles/r01d).  Here lane c of a sub-warp owns child c of the four-wide node: the four
-// lanes fetch the node with two coalesced 64-byte accesses (2 wavefronts instead of 8), each runs ONE slab test, the entry
-// distances are exchanged with three shuffles, every lane computes its child's rank, the nearest child becomes the next node and
-// the other hit children are pushed far-to-near, in parallel, onto the sub-warp's stack in shared memory.  In a leaf, lane c
-// tests primitive c (a leaf holds at most four) and the best candidate is found with two shuffle steps.  Only eight rays share
-// an instruction stream, so far fewer lanes wait for the slowest ray of the warp.
-// Arithmetic per primitive, prio tie-break and the lazy mesh gate are those of the one-lane-per-ray traversal: same hits.
-//
-// MEASURED (B200, synthetic scene, 1080p x 8 spp): bit-identical images, 2 wavefronts per node visit as designed, but 75 vs 175
-// Mpaths/s: with eight instead of ~26 rays per warp and the same 32 warps per SM there are three times fewer independent rays
-// in flight, and the traversal is latency bound.  Kept behind the option "wf_coop" (default off) as a tested experiment.
-// ---------------------------------------------------------------------------------------------------------------------
-constexpr int WF_CSTACK = 32;  // shared-memory stack entries per ray; deeper entries go to a global overflow area
-
-__global__ void __launch_bounds__(WF_THREADS, 4) k_wf_trace_coop(const DScene sc, const WfQueue q, const int *__restrict__ n_rays_ptr,
-                                                                  int *__restrict__ fetch_ptr, unsigned long long *__restrict__ counters,
-                                                                  int2 *__restrict__ overflow, const int refill_groups) {
-    __shared__ int2 s_stack[WF_CSTACK * (WF_THREADS / 4)];
-    const int n = *n_rays_ptr;
-    const int lane = threadIdx.x & 31, sub = lane & 3, gbase = lane & ~3;
-    const unsigned gmask = 0xFu << gbase;
-    const int group_in_block = threadIdx.x >> 2;
-    int2 *const ovf = overflow + ((size_t)blockIdx.x * (WF_THREADS / 4) + group_in_block) * BVH_STACK;
-#define PTB_CSTK(i) (*((i) < WF_CSTACK ? &s_stack[(i) * (WF_THREADS / 4) + group_in_block] : &ovf[(i) - WF_CSTACK]))
-    const float inf = __int_as_float(0x7f800000);
-    unsigned n_nodes = 0, n_prims = 0;
-
-    bool busy = false, exhausted = false;  // busy / cur / sp / best are uniform within a sub-warp
-    int w_next = 0, w_end = 0;
-    int ray_idx = 0;
-    V3 o = mk3(0.f, 0.f, 0.f), d = mk3(0.f, 0.f, 1.f), id = mk3(1.f, 1.f, 1.f), ood = mk3(0.f, 0.f, 0.f);
-    Hit best;
-    best.t = 0.f; best.prio = PRIO_NONE; best.ref = REF_NONE;
-    int cur = BVH_EMPTY_REF, sp = 0, gate_obj = -1;
-    bool gate_pass = false;
-
-#define PTB_CPOP()                                                          \
-    do {                                                                    \
-        cur = BVH_EMPTY_REF;                                                \
-        while (sp > 0) {                                                    \
-            --sp;                                                           \
-            const int2 e_ = PTB_CSTK(sp);                                   \
-            if (__int_as_float(e_.y) <= best.t) { cur = e_.x; break; }      \
-        }                                                                   \
-    } while (0)
-
-    for (;;) {
-        const unsigned busy_mask = __ballot_sync(0xffffffffu, busy);         // four equal bits per sub-warp
-        const int n_idle = (32 - __popc(busy_mask)) >> 2;                    // idle sub-warps
-        if (!exhausted && (n_idle >= refill_groups || busy_mask == 0u)) {
-            if (w_next >= w_end) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(fetch_ptr, WF_CHUNK);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                w_next = base;
-                w_end = min(base + WF_CHUNK, n);
-                if (base >= n) exhausted = true;
-            }
-            // rank of this sub-warp among the idle ones: idle sub-warps below it (count one bit per sub-warp)
-            const unsigned idle_leaders = ~busy_mask & 0x11111111u;
-            const int idx = w_next + __popc(idle_leaders & ((1u << gbase) - 1u));
-            const bool got = !busy && idx < w_end;
-            w_next = min(w_next + n_idle, w_end);
-            if (got) {
-                const float4 qo = __ldcs(&q.o[idx]), qd = __ldcs(&q.d[idx]);
-                o = mk3(qo.x, qo.y, qo.z); d = mk3(qd.x, qd.y, qd.z);
-                ray_idx = idx;
-                best.t = __ldcs(&q.hit_t[idx]); best.ref = __ldcs(&q.hit_ref[idx]); best.prio = __ldcs(&q.hit_prio[idx]);
-                id = mk3(safe_rcp_dir(d.x), safe_rcp_dir(d.y), safe_rcp_dir(d.z));
-                ood = mk3(o.x * id.x, o.y * id.y, o.z * id.z);
-                cur = sc.bvh_root; sp = 0; gate_obj = -1;
-                busy = true;
-            }
-        }
-        if (__ballot_sync(0xffffffffu, busy) == 0u) break;
-        if (busy) {
-            while (cur >= 0) {  // ---- inner node: lane `sub` owns child `sub`
-                const float4 *nd = sc.bvh_nodes + 8 * (size_t)cur;
-                const float4 ca = __ldg(nd + sub), cb = __ldg(nd + 4 + sub);
-                const int ref = __float_as_int(cb.z);
-                float t_in;
-                const bool hit = ref != BVH_EMPTY_REF && slab(ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, id, ood, best.t, t_in);
-                const float t = hit ? t_in : inf;
-                // rank of my child among the hit children (ties by child index)
-                int rank = 0;
-#pragma unroll
-                for (int j = 1; j < 4; ++j) {
-                    const float tj = __shfl_sync(gmask, t, gbase + ((sub + j) & 3));
-                    const int cj = (sub + j) & 3;
-                    rank += (tj < t || (tj == t && cj < sub)) ? 1 : 0;
-                }
-                const unsigned hits = (__ballot_sync(gmask, hit) >> gbase) & 0xFu;
-                const int n_hit = __popc(hits);
-                if (sub == 0) n_nodes++;
-                if (n_hit == 0) {
-                    PTB_CPOP();
-                } else {
-                    // the nearest child is followed, the others are postponed far-to-near (the nearest of them ends on top)
-                    if (hit && rank > 0) PTB_CSTK(sp + (n_hit - 1 - rank)) = make_int2(ref, __float_as_int(t));
-                    const unsigned first = __ballot_sync(gmask, hit && rank == 0);
-                    cur = __shfl_sync(gmask, ref, __ffs(first) - 1);
-                    sp += n_hit - 1;
-                    __syncwarp(gmask);  // the pushes must be visible to the sub-warp's later pops
-                }
-                if ((__popc(__activemask()) >> 2) < 3) break;  // few rays still descending: let the leaf holders get on with it
-            }
-            if (cur < 0 && cur != BVH_EMPTY_REF) {  // ---- leaf: lane `sub` owns primitive `sub`
-                const int code = ~cur;
-                const int first = code >> 3, count = (code & 7) + 1;
-                if (sub == 0) n_prims += count;
-                float ct = inf;
-                uint32_t cprio = PRIO_NONE;
-                int cref = REF_NONE;
-                for (int k0 = 0; k0 < count; k0 += 4) {  // leaves hold at most four primitives by construction; stay general
-                    const int k = first + k0 + sub;
-                    if (k0 + sub < count) {
-                        const float4 A = __ldg(&sc.bvh_tri[2 * (size_t)k]), E1 = __ldg(&sc.bvh_tri[2 * (size_t)k + 1]), E2 = __ldg(&sc.bvh_e2[k]);
-                        const bool is_sphere = __float_as_int(E1.w) < 0;
-                        float tt;
-                        if (is_sphere) tt = sphere_t(xyz(A), E1.x, o, d);
-                        else tt = triangle_t(xyz(A), xyz(E1), xyz(E2), o, d);
-                        const uint32_t prio = (uint32_t)__float_as_int(E2.w);
-                        const bool beats_best = tt < best.t || (tt == best.t && prio < best.prio);
-                        const bool beats_mine = tt < ct || (tt == ct && prio < cprio);
-                        if (tt > 0.0f && beats_best && beats_mine) {
-                            bool ok = true;
-                            if (!is_sphere) {  // mesh gate (mod.rs:267-277), lazily, cached per lane and object
-                                const int obj = __float_as_int(A.w);
-                                if (obj != gate_obj) {
-                                    const float4 g = __ldg(&sc.obj_gate[obj]);
-                                    gate_pass = sphere_gate(xyz(g), g.w, o, d);
-                                    gate_obj = obj;
-                                }
-                                ok = gate_pass;
-                            }
-                            if (ok) { ct = tt; cprio = prio; cref = REF_BVH_BIT | (is_sphere ? REF_SPHERE_BIT : 0) | k; }
-                        }
-                    }
-                }
-                // best candidate of the sub-warp (t, then prio), two butterfly steps
-#pragma unroll
-                for (int m = 1; m <= 2; m <<= 1) {
-                    const float ot = __shfl_xor_sync(gmask, ct, m);
-                    const uint32_t op = __shfl_xor_sync(gmask, cprio, m);
-                    const int orf = __shfl_xor_sync(gmask, cref, m);
-                    if (ot < ct || (ot == ct && op < cprio)) { ct = ot; cprio = op; cref = orf; }
-                }
-                if (cref != REF_NONE) { best.t = ct; best.prio = cprio; best.ref = cref; }
-                PTB_CPOP();
-            }
-            if (cur == BVH_EMPTY_REF) {
-                if (sub == 0) {
-                    __stcs(&q.hit_t[ray_idx], best.t);
-                    __stcs(&q.hit_ref[ray_idx], best.ref);
-                }
-                busy = false;
-            }
-        }
-    }
-#undef PTB_CPOP
-#undef PTB_CSTK
+#undef PTB_STK_LD
+#undef PTB_STK_ST
     for (int off = 16; off > 0; off >>= 1) {
         n_nodes += __shfl_down_sync(0xffffffffu, n_nodes, off);
         n_prims += __shfl_down_sync(0xffffffffu, n_prims, off);
@@ -327,32 +224,33 @@ __global__ void __launch_bounds__(WF_THREADS, 4) k_wf_trace_coop(const DScene sc
 }
 
 // material arm of every queued segment; appends the next bounce
-__global__ void __launch_bounds__(256) k_wf_shade(const DScene sc, const WfQueue q, const int *__restrict__ n_rays_ptr, WfQueue nq,
-                                                  int *__restrict__ n_next_ptr, float4 *__restrict__ slots, unsigned long long n_paths,
-                                                  unsigned npix, unsigned long long s0, unsigned long long seed,
+__global__ void __launch_bounds__(256) k_wf_shade(const DScene sc, const WfQueue q, const int *__restrict__ ctr, WfQueue nq,
+                                                  int *__restrict__ nctr, float4 *__restrict__ slots, int *__restrict__ branch_mask,
+                                                  unsigned n_paths, unsigned npix, unsigned long long s0, unsigned long long seed,
                                                   unsigned long long *__restrict__ segment_counter) {
     extern __shared__ float4 smem[];
     const float4 *s_obj, *s_tri;
     stage_loose(sc, smem, s_obj, s_tri);
-    const int n = *n_rays_ptr;
+    const int n_front = ctr[0], n = n_front + ctr[1];  // entries 0 .. n_front-1 and cap-1 .. cap-n_back
     if (blockIdx.x == 0 && threadIdx.x == 0 && n > 0) atomicAdd(segment_counter, (unsigned long long)n);
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     const int stride = gridDim.x * blockDim.x;
     const int n_round = (n + 31) & ~31;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
-        const bool valid = i < n;
+    for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < n_round; it += stride) {
+        const bool valid = it < n;
+        const int i = it < n_front ? it : q.cap - 1 - (it - n_front);
         int n_out = 0;
         float4 c_o, c_d, c_T, c_L, k_o, k_d, k_T;  // continuation and (optional) transmitted child
-        if (valid) {
-            const float4 qo = __ldg(&q.o[i]), qd = __ldg(&q.d[i]), qT = __ldg(&q.T[i]), qL = __ldg(&q.L[i]);
+        if (valid && PTB_CHECKED(i >= 0 && i < q.cap, PTB_CHK_RAY, sc.check)) {
+            const float4 qo = __ldcs(&q.o[i]), qd = __ldcs(&q.d[i]), qT = __ldcs(&q.T[i]), qL = __ldcs(&q.L[i]);
             const int path = __float_as_int(qo.w), dc = __float_as_int(qd.w);
             const int depth = dc & 0xff, code = dc >> 8;
             const V3 o = mk3(qo.x, qo.y, qo.z), d = mk3(qd.x, qd.y, qd.z), T = mk3(qT.x, qT.y, qT.z);
             V3 L = mk3(qL.x, qL.y, qL.z);
             Hit h;
-            h.t = q.hit_t[i]; h.ref = q.hit_ref[i]; h.prio = 0;
+            h.t = __ldcs(&q.hit_t[i]); h.ref = __ldcs(&q.hit_ref[i]); h.prio = 0;
             bool cont = false;
             if (h.ref != REF_NONE) {
                 const uint32_t pixel = (uint32_t)((unsigned)path % npix);
@@ -379,100 +277,75 @@ __global__ void __launch_bounds__(256) k_wf_shade(const DScene sc, const WfQueue
                         k_o = c_o;
                         k_d = make_float4(so.child_d.x, so.child_d.y, so.child_d.z, __int_as_float(new_depth | (child << 8)));
                         k_T = make_float4(so.child_T.x, so.child_T.y, so.child_T.z, 0.f);
+                        if (PTB_CHECKED((unsigned)path < n_paths && child >= 1 && child <= 3, PTB_CHK_SLOT, sc.check))
+                            atomicOr(&branch_mask[path], 1 << child);  // branch `child` of this path now exists
                     }
                 }
             }
-            if (!cont) slots[(size_t)code * n_paths + (size_t)path] = make_float4(L.x, L.y, L.z, 0.f);  // branch finished
+            if (!cont && PTB_CHECKED((unsigned)path < n_paths && (unsigned)code < 4u, PTB_CHK_SLOT, sc.check))
+                slots[(size_t)code * n_paths + (size_t)path] = make_float4(L.x, L.y, L.z, 0.f);  // branch finished
         }
-        // one atomic per warp for all appended entries
+        // closest hit of the new segments over the shared-memory list (so the trace kernel only does BVH work), then one atomic
+        // per warp for everything the warp appends
         const unsigned m1 = __ballot_sync(0xffffffffu, n_out >= 1), m2 = __ballot_sync(0xffffffffu, n_out == 2);
-        const int total = __popc(m1) + __popc(m2);
-        if (total) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(n_next_ptr, total);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (n_out >= 1) {
-                const int j = base + __popc(m1 & lt_mask);
-                nq.o[j] = c_o; nq.d[j] = c_d; nq.T[j] = c_T; nq.L[j] = c_L;
-                store_loose_hit(nq, j, s_obj, mk3(c_o.x, c_o.y, c_o.z), mk3(c_d.x, c_d.y, c_d.z), m1);
-            }
-            if (n_out == 2) {
-                const int j = base + __popc(m1) + __popc(m2 & lt_mask);
-                nq.o[j] = k_o; nq.d[j] = k_d; nq.T[j] = k_T; nq.L[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                store_loose_hit(nq, j, s_obj, mk3(k_o.x, k_o.y, k_o.z), mk3(k_d.x, k_d.y, k_d.z), m2);
-            }
+        if ((m1 | m2) == 0u) continue;
+        Hit h1, h2;
+        bool f1 = false, f2 = false;
+        if (n_out >= 1) f1 = loose_hit(sc, s_obj, mk3(c_o.x, c_o.y, c_o.z), mk3(c_d.x, c_d.y, c_d.z), m1, h1);
+        if (m2 != 0u && n_out == 2) f2 = loose_hit(sc, s_obj, mk3(k_o.x, k_o.y, k_o.z), mk3(k_d.x, k_d.y, k_d.z), m2, h2);
+        int j1, j2;
+        append2(sc, nq, nctr, n_out >= 1, f1, n_out == 2, f2, lt_mask, j1, j2);
+        if (j1 >= 0) {
+            nq.o[j1] = c_o; nq.d[j1] = c_d; nq.T[j1] = c_T; nq.L[j1] = c_L;
+            nq.hit_t[j1] = h1.t; nq.hit_ref[j1] = h1.ref; nq.hit_prio[j1] = h1.prio;
+        }
+        if (j2 >= 0) {
+            nq.o[j2] = k_o; nq.d[j2] = k_d; nq.T[j2] = k_T; nq.L[j2] = make_float4(0.f, 0.f, 0.f, 0.f);
+            nq.hit_t[j2] = h2.t; nq.hit_ref[j2] = h2.ref; nq.hit_prio[j2] = h2.prio;
         }
     }
 }
 
-// Ray reordering between bounces (option wf_sort, default off).  Sort key of a queued ray: rays that start close together and
-// point into the same octant visit the same BVH nodes, so a warp tracing 32 of them could share its node fetches.
-// 21-bit Morton code of the origin's cell in a 128^3 grid over the scene box + 3 bits of direction signs.  Only the ORDER in
-// which rays are traced depends on it: hits, shading and the per-path sums do not (bit-identical images, tested).
-// MEASURED (B200, profiles/r01j_ray_sort_experiment.md): synthetic 1.31 M triangles 4K: 179 -> 153 (octant-major) / 163 (cell-major)
-// Mpaths/s; mesh.json 1080p: 707 -> 343 / 357.  Diffuse bounces inside one octant still diverge within a few levels of a deep BVH,
-// so the traversal gains a few per cent while key + radix sort + length read-back + scattered ray fetch cost 0.7-1 ms per bounce.
-__device__ __forceinline__ unsigned spread7(unsigned v) {  // bit i -> bit 3i (i < 10)
-    v = (v ^ (v << 16)) & 0xff0000ffu;
-    v = (v ^ (v << 8)) & 0x0300f00fu;
-    v = (v ^ (v << 4)) & 0x030c30c3u;
-    v = (v ^ (v << 2)) & 0x09249249u;
-    return v;
-}
-__global__ void __launch_bounds__(256) k_wf_ray_keys(const DScene sc, const WfQueue q, int n, int mode, unsigned *__restrict__ keys,
-                                                     int *__restrict__ idx) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float4 o = __ldg(&q.o[i]), d = __ldg(&q.d[i]);
-    const float fx = fminf(fmaxf((o.x - sc.world_lo.x) * sc.world_inv.x, 0.f), 1.f);
-    const float fy = fminf(fmaxf((o.y - sc.world_lo.y) * sc.world_inv.y, 0.f), 1.f);
-    const float fz = fminf(fmaxf((o.z - sc.world_lo.z) * sc.world_inv.z, 0.f), 1.f);
-    const unsigned cx = min((unsigned)(fx * 128.f), 127u), cy = min((unsigned)(fy * 128.f), 127u), cz = min((unsigned)(fz * 128.f), 127u);
-    const unsigned cell = spread7(cx) | (spread7(cy) << 1) | (spread7(cz) << 2);
-    const unsigned oct = (d.x < 0.f ? 1u : 0u) | (d.y < 0.f ? 2u : 0u) | (d.z < 0.f ? 4u : 0u);
-    keys[i] = mode == 2 ? ((cell << 3) | oct) : ((oct << 21) | cell);
-    idx[i] = i;
-}
-
 // radiance_v += radiance(sample) for the K samples of the batch, in sample order (mod.rs:846)
-__global__ void __launch_bounds__(256) k_wf_accumulate(const float4 *__restrict__ slots, unsigned long long n_paths, unsigned npix,
-                                                       unsigned K, float *__restrict__ sum_rgb, const int fb_zero) {
+__global__ void __launch_bounds__(256) k_wf_accumulate(const float4 *__restrict__ slots, const int *__restrict__ branch_mask,
+                                                       unsigned n_paths, unsigned npix, unsigned K, float *__restrict__ sum_rgb,
+                                                       const int fb_zero) {
     const unsigned stride = gridDim.x * blockDim.x;
     for (unsigned pixel = blockIdx.x * blockDim.x + threadIdx.x; pixel < npix; pixel += stride) {
         float *fb = sum_rgb + 3ull * pixel;
         V3 acc = fb_zero ? mk3(0.f, 0.f, 0.f) : mk3(fb[0], fb[1], fb[2]);
         for (unsigned k = 0; k < K; ++k) {
             const size_t p = (size_t)k * npix + pixel;
-            const float4 a = slots[p], b = slots[n_paths + p], c = slots[2 * n_paths + p], e = slots[3 * n_paths + p];
-            const V3 L = ((mk3(a.x, a.y, a.z) + mk3(b.x, b.y, b.z)) + mk3(c.x, c.y, c.z)) + mk3(e.x, e.y, e.z);
+            const int mask = __ldcs(&branch_mask[p]);
+            const float4 a = __ldcs(&slots[p]);
+            V3 L = mk3(a.x, a.y, a.z);
+            if (mask) {  // the path split: ((L0 + L1) + L2) + L3, absent branches count as zero
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 b = (mask & 2) ? __ldcs(&slots[n_paths + p]) : z;
+                const float4 c = (mask & 4) ? __ldcs(&slots[2 * (size_t)n_paths + p]) : z;
+                const float4 e = (mask & 8) ? __ldcs(&slots[3 * (size_t)n_paths + p]) : z;
+                L = ((L + mk3(b.x, b.y, b.z)) + mk3(c.x, c.y, c.z)) + mk3(e.x, e.y, e.z);
+            }
             acc = acc + L;
         }
         fb[0] = acc.x; fb[1] = acc.y; fb[2] = acc.z;
     }
 }
 
-size_t loose_smem(const DScene &sc) { return loose_smem_bytes(sc); }
+template <typename T>
+cudaError_t wf_alloc(T *&p, size_t n) { return cudaMalloc(reinterpret_cast<void **>(&p), n * sizeof(T)); }
+
+constexpr size_t WF_CTR_INTS = (size_t)WF_CTR_STRIDE * (WF_MAX_BOUNCES + 2);
 
 }  // namespace
 
 void wf_release(WfWorkspace &w) {
     for (int b = 0; b < 2; ++b) {
-        if (w.q[b].o) cudaFree(w.q[b].o);
-        if (w.q[b].d) cudaFree(w.q[b].d);
-        if (w.q[b].T) cudaFree(w.q[b].T);
-        if (w.q[b].L) cudaFree(w.q[b].L);
-        if (w.q[b].hit_t) cudaFree(w.q[b].hit_t);
-        if (w.q[b].hit_ref) cudaFree(w.q[b].hit_ref);
-        if (w.q[b].hit_prio) cudaFree(w.q[b].hit_prio);
+        WfQueue &q = w.q[b];
+        cudaFree(q.o); cudaFree(q.d); cudaFree(q.T); cudaFree(q.L);
+        cudaFree(q.hit_t); cudaFree(q.hit_ref); cudaFree(q.hit_prio);
     }
-    if (w.slots) cudaFree(w.slots);
-    if (w.counters) cudaFree(w.counters);
-    if (w.overflow) cudaFree(w.overflow);
-    for (int b = 0; b < 2; ++b) {
-        if (w.sort_keys[b]) cudaFree(w.sort_keys[b]);
-        if (w.sort_idx[b]) cudaFree(w.sort_idx[b]);
-    }
-    if (w.sort_tmp) cudaFree(w.sort_tmp);
+    cudaFree(w.slots); cudaFree(w.branch_mask); cudaFree(w.counters);
     w = WfWorkspace{};
 }
 
@@ -482,112 +355,95 @@ static cudaError_t wf_reserve(WfWorkspace &w, size_t n_paths) {
     const size_t cap = 4 * n_paths;  // every path can split twice (mod.rs:775-786): at most 4 live branches
     cudaError_t e;
     for (int b = 0; b < 2; ++b) {
-        if ((e = cudaMalloc((void **)&w.q[b].o, cap * sizeof(float4))) != cudaSuccess) return e;
-        if ((e = cudaMalloc((void **)&w.q[b].d, cap * sizeof(float4))) != cudaSuccess) return e;
-        if ((e = cudaMalloc((void **)&w.q[b].T, cap * sizeof(float4))) != cudaSuccess) return e;
-        if ((e = cudaMalloc((void **)&w.q[b].L, cap * sizeof(float4))) != cudaSuccess) return e;
-        if ((e = cudaMalloc((void **)&w.q[b].hit_t, cap * sizeof(float))) != cudaSuccess) return e;
-        if ((e = cudaMalloc((void **)&w.q[b].hit_ref, cap * sizeof(int))) != cudaSuccess) return e;
-        if ((e = cudaMalloc((void **)&w.q[b].hit_prio, cap * sizeof(unsigned))) != cudaSuccess) return e;
+        WfQueue &q = w.q[b];
+        if ((e = wf_alloc(q.o, cap)) != cudaSuccess) return e;
+        if ((e = wf_alloc(q.d, cap)) != cudaSuccess) return e;
+        if ((e = wf_alloc(q.T, cap)) != cudaSuccess) return e;
+        if ((e = wf_alloc(q.L, cap)) != cudaSuccess) return e;
+        if ((e = wf_alloc(q.hit_t, cap)) != cudaSuccess) return e;
+        if ((e = wf_alloc(q.hit_ref, cap)) != cudaSuccess) return e;
+        if ((e = wf_alloc(q.hit_prio, cap)) != cudaSuccess) return e;
+        q.cap = (int)cap;
     }
-    if ((e = cudaMalloc((void **)&w.slots, 4 * n_paths * sizeof(float4))) != cudaSuccess) return e;
-    if ((e = cudaMalloc((void **)&w.counters, 2 * (WF_MAX_BOUNCES + 2) * sizeof(int))) != cudaSuccess) return e;
+    if ((e = wf_alloc(w.slots, 4 * n_paths)) != cudaSuccess) return e;
+    if ((e = wf_alloc(w.branch_mask, n_paths)) != cudaSuccess) return e;
+    if ((e = wf_alloc(w.counters, WF_CTR_INTS)) != cudaSuccess) return e;
     w.cap_paths = n_paths;
     return cudaSuccess;
 }
 
-// renders samples [a.spp_begin, a.spp_begin + a.spp_count) of every pixel into a.sum_rgb; returns the number of kernels launched
-cudaError_t wavefront_render(const DScene &sc, const RenderArgs &a, WfWorkspace &w, int sm_count, size_t target_paths, int refill,
-                             int descend_min, int coop, int sort_mode, cudaStream_t st,
+namespace {
+
+struct TraceLaunch {
+    void (*kern)(const DScene, const WfQueue, const int *, int *, unsigned long long *, int, int) = nullptr;
+    int threads = 256, blocks = 0;
+    size_t smem = 0;
+};
+
+template <int THREADS>
+cudaError_t trace_config(const DScene &sc, int sm_count, TraceLaunch &t) {
+    t.kern = k_wf_trace<THREADS>;
+    t.threads = THREADS;
+    t.smem = sizeof(float4) * TOP_PITCH * (size_t)sc.n_bvh_top + sizeof(int2) * WF_SSTACK * THREADS;
+    cudaError_t e = cudaFuncSetAttribute(t.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, t.kern, THREADS, t.smem)) != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    t.blocks = sm_count * per_sm;  // persistent grid: a whole number of resident CTAs per SM
+    return cudaSuccess;
+}
+
+}  // namespace
+
+// renders samples [a.spp_begin, a.spp_begin + a.spp_count) of every pixel into a.sum_rgb; adds the kernels launched to *launches
+cudaError_t wavefront_render(const DScene &sc, const RenderArgs &a, WfWorkspace &w, int sm_count, const WfOptions &opt, cudaStream_t st,
                              unsigned *launches) {
     const unsigned npix = (unsigned)a.width * (unsigned)a.height;
-    unsigned K = (unsigned)std::max<size_t>(1, target_paths / npix);
+    unsigned K = (unsigned)std::max<size_t>(1, opt.target_paths / npix);
     if ((unsigned long long)K > a.spp_count) K = (unsigned)a.spp_count;
     if (K == 0) return cudaSuccess;
     const size_t n_paths = (size_t)npix * K;
-    if (n_paths > (1ull << 29)) return cudaErrorInvalidValue;  // queue indices are 32-bit ints, 4 branches per path
+    if (n_paths >= (1ull << 29)) return cudaErrorInvalidValue;  // queue indices are 32-bit ints, 4 branches per path
     cudaError_t e = wf_reserve(w, n_paths);
     if (e != cudaSuccess) return e;
-    const size_t smem = loose_smem(sc);
+    const size_t smem = loose_smem_bytes(sc);
     if ((e = cudaFuncSetAttribute(k_wf_generate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_wf_shade, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-    int trace_per_sm = 0;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_per_sm, k_wf_trace, WF_THREADS, 0)) != cudaSuccess) return e;
-    if (trace_per_sm < 1) return cudaErrorLaunchOutOfResources;
-    int coop_per_sm = 0;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&coop_per_sm, k_wf_trace_coop, WF_THREADS, 0)) != cudaSuccess) return e;
-    if (coop_per_sm < 1) return cudaErrorLaunchOutOfResources;
-    const int trace_blocks = sm_count * trace_per_sm, coop_blocks = sm_count * coop_per_sm, wide_blocks = sm_count * 8;
-    if (coop) {
-        const size_t need = (size_t)coop_blocks * (WF_THREADS / 4) * BVH_STACK;
-        if (w.cap_overflow < need) {
-            if (w.overflow) cudaFree(w.overflow);
-            w.overflow = nullptr; w.cap_overflow = 0;
-            if ((e = cudaMalloc((void **)&w.overflow, need * sizeof(int2))) != cudaSuccess) return e;
-            w.cap_overflow = need;
-        }
+    const bool has_bvh = sc.bvh_root != BVH_EMPTY_REF;
+    TraceLaunch tl;
+    if (has_bvh) {
+        // the CTA size trades copies of the top levels per SM against scheduling granularity (opt.trace_threads: 256, 512 or 1024)
+        if (opt.trace_threads >= 1024) e = trace_config<1024>(sc, sm_count, tl);
+        else if (opt.trace_threads >= 512) e = trace_config<512>(sc, sm_count, tl);
+        else e = trace_config<256>(sc, sm_count, tl);
+        if (e != cudaSuccess) return e;
     }
-
-    // ray reordering only pays where rays walk a BVH, and the cooperative kernel has its own fetch logic
-    const bool sorting = sort_mode != 0 && !coop && sc.bvh_root != BVH_EMPTY_REF;
-    if (sorting && w.cap_sort < 4 * n_paths) {
-        for (int b = 0; b < 2; ++b) {
-            if (w.sort_keys[b]) cudaFree(w.sort_keys[b]);
-            if (w.sort_idx[b]) cudaFree(w.sort_idx[b]);
-            w.sort_keys[b] = nullptr; w.sort_idx[b] = nullptr;
-        }
-        if (w.sort_tmp) cudaFree(w.sort_tmp);
-        w.sort_tmp = nullptr; w.cap_sort = 0;
-        const size_t cap = 4 * n_paths;
-        for (int b = 0; b < 2; ++b) {
-            if ((e = cudaMalloc((void **)&w.sort_keys[b], cap * sizeof(unsigned))) != cudaSuccess) return e;
-            if ((e = cudaMalloc((void **)&w.sort_idx[b], cap * sizeof(int))) != cudaSuccess) return e;
-        }
-        w.sort_tmp_bytes = 0;
-        if ((e = cub::DeviceRadixSort::SortPairs(nullptr, w.sort_tmp_bytes, w.sort_keys[0], w.sort_keys[1], w.sort_idx[0], w.sort_idx[1],
-                                                 (long long)cap, 0, 24, st)) != cudaSuccess) return e;
-        if ((e = cudaMalloc(&w.sort_tmp, std::max<size_t>(w.sort_tmp_bytes, 16))) != cudaSuccess) return e;
-        w.cap_sort = cap;
-    }
+    auto blocks_for = [&](size_t n) { return (unsigned)std::max<size_t>(1, std::min<size_t>((n + 255) / 256, (size_t)sm_count * 8)); };
 
     unsigned long long done = 0;
     while (done < a.spp_count) {
         const unsigned k_now = (unsigned)std::min<unsigned long long>(K, a.spp_count - done);
         const size_t paths_now = (size_t)npix * k_now;
         const unsigned long long s0 = a.spp_begin + done;
-        // counters[2*b] = entries of bounce b's queue, counters[2*b+1] = its fetch cursor
-        if ((e = cudaMemsetAsync(w.counters, 0, 2 * (WF_MAX_BOUNCES + 2) * sizeof(int), st)) != cudaSuccess) return e;
-        const int first = (int)paths_now;
-        if ((e = cudaMemcpyAsync(w.counters, &first, sizeof(int), cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
-        if ((e = cudaMemsetAsync(w.slots, 0, 4 * n_paths * sizeof(float4), st)) != cudaSuccess) return e;
-        k_wf_generate<<<wide_blocks, 256, smem, st>>>(sc, a.width, a.height, npix, s0, k_now, a.seed, w.q[0]);
+        const unsigned wide = blocks_for(paths_now);
+        // per bounce b: ctr[4b] = entries at the front of its queue (to trace), [4b+1] = entries at its back, [4b+2] = the trace kernel's fetch cursor
+        if ((e = cudaMemsetAsync(w.counters, 0, WF_CTR_INTS * sizeof(int), st)) != cudaSuccess) return e;
+        k_wf_generate<<<wide, 256, smem, st>>>(sc, a.width, a.height, npix, s0, k_now, a.seed, w.q[0], w.branch_mask, w.counters);
         (*launches)++;
-        const int *order = nullptr;  // bounce 0: camera rays, generated in pixel order, are coherent as they are
         for (int b = 0; b < WF_MAX_BOUNCES; ++b) {
             const WfQueue &cur = w.q[b & 1], &nxt = w.q[(b + 1) & 1];
-            if (coop)
-                k_wf_trace_coop<<<coop_blocks, WF_THREADS, 0, st>>>(sc, cur, w.counters + 2 * b, w.counters + 2 * b + 1, a.segment_counter,
-                                                                     w.overflow, 2);
-            else
-                k_wf_trace<<<trace_blocks, WF_THREADS, 0, st>>>(sc, cur, w.counters + 2 * b, w.counters + 2 * b + 1, a.segment_counter, refill,
-                                                                descend_min, order);
-            k_wf_shade<<<wide_blocks, 256, smem, st>>>(sc, cur, w.counters + 2 * b, nxt, w.counters + 2 * (b + 1), w.slots,
-                                                       n_paths, npix, s0, a.seed, a.segment_counter);
-            *launches += 2;
-            if (sorting && b + 1 < WF_MAX_BOUNCES) {
-                int n_next = 0;  // the sort needs the queue length on the host: one 4-byte read-back per bounce
-                if ((e = cudaMemcpyAsync(&n_next, w.counters + 2 * (b + 1), sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
-                if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
-                if (n_next <= 0) break;  // every branch has ended: the remaining bounces would be empty launches
-                k_wf_ray_keys<<<(n_next + 255) / 256, 256, 0, st>>>(sc, nxt, n_next, sort_mode, w.sort_keys[0], w.sort_idx[0]);
+            int *ctr = w.counters + WF_CTR_STRIDE * b;
+            if (has_bvh) {
+                tl.kern<<<tl.blocks, tl.threads, tl.smem, st>>>(sc, cur, ctr, ctr + 2, a.segment_counter, opt.refill, opt.descend_min);
                 (*launches)++;
-                size_t tmp = w.sort_tmp_bytes;
-                if ((e = cub::DeviceRadixSort::SortPairs(w.sort_tmp, tmp, w.sort_keys[0], w.sort_keys[1], w.sort_idx[0], w.sort_idx[1],
-                                                         (long long)n_next, 0, 24, st)) != cudaSuccess) return e;
-                order = w.sort_idx[1];
             }
+            k_wf_shade<<<wide, 256, smem, st>>>(sc, cur, ctr, nxt, ctr + WF_CTR_STRIDE, w.slots, w.branch_mask, (unsigned)n_paths, npix, s0,
+                                                a.seed, a.segment_counter);
+            (*launches)++;
         }
-        k_wf_accumulate<<<wide_blocks, 256, 0, st>>>(w.slots, n_paths, npix, k_now, a.sum_rgb, (a.fb_zero && done == 0) ? 1 : 0);
+        k_wf_accumulate<<<wide, 256, 0, st>>>(w.slots, w.branch_mask, (unsigned)n_paths, npix, k_now, a.sum_rgb,
+                                              (a.fb_zero && done == 0) ? 1 : 0);
         (*launches)++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         done += k_now;

@@ -10,6 +10,7 @@
 namespace ptb {
 
 constexpr int WF_MAX_BOUNCES = 12;  // = MAX_DEPTH (mod.rs:661): a branch makes at most 12 radiance() calls
+constexpr int WF_CTR_STRIDE = 4;    // ints per bounce in the counter block: front count, back count (one 64-bit word), fetch cursor, -
 
 struct WfQueue {   // SoA of ray segments: 4 x float4 per entry
     float4 *o = nullptr;  // origin | path id (sample offset * npix + pixel)
@@ -21,25 +22,28 @@ struct WfQueue {   // SoA of ray segments: 4 x float4 per entry
     float *hit_t = nullptr;
     int *hit_ref = nullptr;
     unsigned *hit_prio = nullptr;
+    // Filled from both ends: entries 0, 1, ... are the segments whose [0, hit_t] touches the BVH's root box (the only ones
+    // k_wf_trace looks at), entries cap-1, cap-2, ... the others.
+    int cap = 0;          // entries allocated
 };
 
 struct WfWorkspace {
     WfQueue q[2];
-    float4 *slots = nullptr;  // [4 branches][n_paths] finished branch sums
-    int *counters = nullptr;  // per bounce: queue length, fetch cursor
-    int2 *overflow = nullptr; // cooperative trace kernel: stack entries beyond the shared-memory part, per sub-warp
-    size_t cap_overflow = 0;
+    float4 *slots = nullptr;   // [4 branches][n_paths] finished branch sums
+    int *branch_mask = nullptr; // [n_paths] which of the branches 1..3 exist (bit c): set by the split that creates them
+    int *counters = nullptr;   // WF_CTR_STRIDE ints per bounce
     size_t cap_paths = 0;
-    // ray reordering between bounces (wf_sort): keys / queue indices, double-buffered for the radix sort, and its scratch
-    unsigned *sort_keys[2] = {nullptr, nullptr};
-    int *sort_idx[2] = {nullptr, nullptr};
-    void *sort_tmp = nullptr;
-    size_t sort_tmp_bytes = 0, cap_sort = 0;
+};
+
+struct WfOptions {
+    size_t target_paths = 1u << 25;  // paths in flight per batch (measured on B200: 2^23 -> 2^25 = +15 % synthetic, +8 % mesh.json; 2^26 +3 % more)
+    int refill = 8;                  // idle lanes of a warp that trigger a refill from the queue
+    int descend_min = 12;            // lanes that must still be descending for the node loop to go on
+    int trace_threads = 512;         // CTA size of the trace kernel (256, 512 or 1024): copies of the BVH's top levels per SM
 };
 
 void wf_release(WfWorkspace &w);
-cudaError_t wavefront_render(const DScene &sc, const RenderArgs &a, WfWorkspace &w, int sm_count, size_t target_paths, int refill,
-                             int descend_min, int coop, int sort_mode, cudaStream_t st,
+cudaError_t wavefront_render(const DScene &sc, const RenderArgs &a, WfWorkspace &w, int sm_count, const WfOptions &opt, cudaStream_t st,
                              unsigned *launches);
 
 }  // namespace ptb

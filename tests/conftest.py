@@ -41,6 +41,22 @@ def kat_scene(tmp_path):
     return make
 
 
+def pytest_collection_modifyitems(config, items):
+    """GPU tests skip (instead of erroring) on a machine without a CUDA device or without the built library."""
+    n_dev = 0
+    try:
+        import path_tracer_rust_b200 as P
+        n_dev = P.load_library().ptb_device_count()
+    except Exception:
+        n_dev = 0
+    if n_dev > 0:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device (or libptb.so not built)")
+    for it in items:
+        if "gpu" in it.keywords:
+            it.add_marker(skip)
+
+
 @pytest.fixture(scope="session", autouse=True)
 def ensure_built():
     """libptb.so, the render CLI and the oracle are build products (git-ignored); build them if this checkout has none."""

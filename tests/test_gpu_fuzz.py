@@ -92,11 +92,14 @@ def test_random_scene_matches_oracle(tmp_path, idx, n_spheres, n_inline, n_file_
     ref_fb, ref_st = osc.render_sum(W, H, spp, seed=idx)
     for opts in ({"integrator": 1}, {"integrator": 2, "wavefront_paths": 5000},
                  {"integrator": 1, "bvh_min_tris": 1e18, "bvh_min_spheres": 1e18}, {"integrator": 2, "bvh_min_tris": 2, "bvh_min_spheres": 2},
-                 {"integrator": 2, "wf_coop": 1, "bvh_leaf_max": 4, "bvh_min_tris": 2, "bvh_min_spheres": 2},
+                 {"integrator": 2, "bvh_leaf_max": 4, "bvh_min_tris": 2, "bvh_min_spheres": 2},
+                 {"integrator": 2, "wf_refill": 1, "wf_descend_min": 30, "bvh_top_levels": 2, "bvh_min_tris": 2, "bvh_min_spheres": 2,
+                  "wavefront_paths": 7000},
                  {"integrator": 1, "quad_min_ratio": 0.0},      # every one-pair mesh takes the vote-free path, failing gates included
                  {"integrator": 2, "quad_min_ratio": 1e9},      # none does
-                 {"integrator": 2, "wf_sort": 1, "bvh_min_tris": 2, "bvh_min_spheres": 2},
-                 {"integrator": 2, "wf_sort": 2, "wavefront_paths": 5000, "bvh_min_tris": 2, "bvh_min_spheres": 2}):
+                 {"integrator": 2, "bvh_top_levels": 3, "wf_trace_threads": 512, "bvh_min_tris": 2, "bvh_min_spheres": 2},
+                 {"integrator": 2, "bvh_top_levels": 5, "wf_trace_threads": 1024, "bvh_leaf_max": 1, "wavefront_paths": 5000,
+                  "bvh_min_tris": 2, "bvh_min_spheres": 2}):
         be = P.Backend(0)
         try:
             for k, v in opts.items():

@@ -201,6 +201,86 @@ def test_render_mirror_of_reference_api(be):
     assert rgb[:5].mean() > rgb[-5:].mean()
 
 
+def test_progressive_previews_converge_and_final_is_unchanged(be):
+    """RenderUpdate{progress, image} (mod.rs:882-886, 965-982): previews arrive during the render with growing progress, each is
+    the clamped mean of the samples finished so far (bit-identical to rendering exactly that many samples), and the final image
+    is bit-identical to the unpreviewed render."""
+    import path_tracer_rust_b200 as P
+    be.upload_scene(P.Scene.load("cornell"))
+    W, H, spp = 640, 480, 4096          # 2^28 samples per launch when watched: 873 spp per launch, so four previews
+    plain = be.render(W, H, spp, seed=11)
+    seen = []
+    got = be.render_progressive(W, H, spp, lambda img, d, t: seen.append((img, d, t)), preview_interval_ms=0.0, seed=11)
+    assert np.array_equal(bits(got), bits(plain))
+    assert len(seen) >= 3 and all(t == spp for _, _, t in seen)
+    dones = [d for _, d, _ in seen]
+    assert dones == sorted(dones) and len(set(dones)) == len(dones) and 0 < dones[0] and dones[-1] < spp
+    img, d, _ = seen[0]
+    assert img.shape == (W * H, 3) and img.min() >= 0.0 and img.max() <= 1.0
+    assert np.array_equal(bits(img), bits(be.render(W, H, d, seed=11)))      # the partial mean of samples [0, d)
+    err = [float(np.abs(i - plain).mean()) for i, _, _ in seen]
+    assert err[-1] < err[0]                                                  # converging towards the final image
+    # the render() mirror forwards them as RenderUpdate.image
+    ups = []
+    cfg = P.RenderConfig(samples_per_pixel=spp, resolution=P.Resolution(height=H, width=W), scene=P.Scene.load("cornell"), seed=11)
+    done = P.render(cfg, send_update_progress=ups.append, backend=be, progress_interval=0.0)
+    assert np.array_equal(bits(done.image.pixels), bits(plain))
+    assert len(ups) >= 3 and all(u.image is not None and 0.0 < u.progress < 1.0 for u in ups)
+    assert [u.progress for u in ups] == sorted(u.progress for u in ups)
+
+
+def test_unwatched_render_does_not_sync_per_launch(be):
+    """ptb_render without cancel / samples_done must not turn interactive: one launch covers 2^31 samples."""
+    import path_tracer_rust_b200 as P
+    be.upload_scene(P.Scene.load("cornell"))
+    be.set_option("integrator", 1)
+    try:
+        be.render(640, 480, 2000, seed=1)
+        assert be.stats()["kernel_launches"] == 2                           # one k_render + the resolve
+        done = C.c_uint64(0)
+        be.render(640, 480, 2000, seed=1, samples_done=done)
+        assert be.stats()["kernel_launches"] == 4 and done.value == 640 * 480 * 2000   # watched: 873 spp per launch
+    finally:
+        be.set_option("integrator", 0)
+
+
+def test_multi_gpu_context_bit_exact():
+    """ptb_create_multi (the seam stays render(), mod.rs:928-934): one context, several GPUs, no torch.  The image must
+    equal the oracle's per-device partial sums added in device order, resolved -- and the single-GPU image up to that order."""
+    import path_tracer_rust_b200 as P
+    import path_tracer_rust_b200.api as A
+    from path_tracer_rust_b200.distributed import shard_samples
+    n = P.load_library().ptb_device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 CUDA devices")
+    G = 2 if n < 4 else 4
+    W, H, spp = 96, 64, 13
+    for sid in ("cornell", "mesh"):
+        sc = P.Scene.load(sid)
+        osc = O.OracleScene(scene_path(sid))
+        mb = P.Backend(list(range(G)))
+        try:
+            mb.upload_scene(sc)
+            acc = None
+            for g in range(G):
+                b, c = shard_samples(spp, G, g)
+                part = osc.render_sum(W, H, c, spp_begin=b, seed=5)[0]
+                acc = part if acc is None else (acc + part).astype(f32)
+            got_sum = mb.render(W, H, spp, seed=5, out_kind=A.PTB_OUT_SUM)
+            assert np.array_equal(bits(got_sum), bits(acc)), sid
+            st = mb.stats()
+            assert st["samples"] == W * H * spp and st["segments"] == int(osc.render_sum(W, H, spp, seed=5)[1][0])
+            got = mb.render(W, H, spp, seed=5)
+            assert np.array_equal(bits(got), bits(O.resolve(acc, spp))), sid
+            # progress and previews through the multi context
+            done = C.c_uint64(0)
+            seen = []
+            mb.render_progressive(W, H, spp, lambda img, d, t: seen.append(d), preview_interval_ms=0.0, seed=5, samples_done=done)
+            assert done.value == W * H * spp
+        finally:
+            mb.close()
+
+
 # ---- BVH: same closest hit as the brute-force scan and as the oracle, bit for bit -------------------------------
 @pytest.fixture(scope="module")
 def synthetic_small(tmp_path_factory):

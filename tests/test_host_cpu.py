@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol(P):
         assert hasattr(L, name), name
     import path_tracer_rust_b200.api as A
     assert sorted(A.ABI_SYMBOLS) == declared
-    assert L.ptb_abi_version() == 1
+    assert L.ptb_abi_version() == 2
 
 
 def test_no_cpu_fallback(P):

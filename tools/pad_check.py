@@ -7,6 +7,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import numpy as np, ctypes as C
+import os
+os.environ.setdefault('PTB_LIBRARY', os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'path_tracer_rust_b200', 'libptb_exp.so'))  # bvh_pad_scale_UNSAFE only exists in the experiments build
 import path_tracer_rust_b200 as P
 f32=np.float32
 rng = np.random.default_rng(2024)

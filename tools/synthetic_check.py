@@ -11,6 +11,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
+import os
+os.environ.setdefault('PTB_LIBRARY', os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'path_tracer_rust_b200', 'libptb_exp.so'))  # bvh_pad_scale_UNSAFE only exists in the experiments build
 import path_tracer_rust_b200 as P
 import path_tracer_rust_b200.api as A
 

@@ -75,11 +75,12 @@ struct ptb_ctx {
     BvhDevice bvh;
     BvhOptions bvh_opt;
     WfWorkspace wf;
-    int integrator = 0;             // 0 = auto (wavefront when the scene has a BVH), 1 = megakernel, 2 = wavefront
+    int integrator = 0;             // 0 = auto, 1 = megakernel (one lane per pixel), 2 = wavefront, 3 = sample-parallel megakernel
     WfOptions wf_opt;               // wavefront integrator tuning (paths in flight, refill threshold, trace CTA size)
     int regen_batch = REGEN_BATCH;
     double quad_min_ratio = 0.125;  // one-pair meshes with gate radius >= this x scene diagonal are tested without the warp vote
     DevBuf<float> fb, scratch_f, preview;
+    DevBuf<float4> sample_L;        // sample-parallel megakernel: per-sample radiance of one launch
     DevBuf<int> check_word;         // PTB_CHECK build: first bounds violation seen by a kernel (0 = none)
     float *preview_host = nullptr;  // pinned staging buffer of the progressive previews
     size_t preview_host_floats = 0;
@@ -196,7 +197,7 @@ extern "C" void ptb_destroy(ptb_ctx *ctx) {
     cudaSetDevice(ctx->device);
     for (float *p : ctx->peer_stage) cudaFree(p);
     if (ctx->preview_host) cudaFreeHost(ctx->preview_host);
-    ctx->preview.release(); ctx->check_word.release();
+    ctx->preview.release(); ctx->check_word.release(); ctx->sample_L.release();
     ctx->loose_obj.release(); ctx->loose_tri.release(); ctx->obj_gate.release(); ctx->mat_color.release();
     ctx->mat_emis.release(); ctx->fb.release(); ctx->scratch_f.release(); ctx->scratch_i.release();
     ctx->tile_counter.release(); ctx->seg_counter.release();
@@ -627,11 +628,13 @@ int render_device_impl(ptb_ctx *ctx, int width, int height, uint64_t spp_begin, 
     CU(ctx, cudaMemsetAsync(ctx->seg_counter.p, 0, 4 * sizeof(unsigned long long), st));
     CU(ctx, cudaEventRecord(ctx->ev0, st));
     const uint64_t npix = static_cast<uint64_t>(width) * static_cast<uint64_t>(height);
-    // auto: the wavefront integrator when the scene has a BVH, and also for images too small to give every resident
-    // megakernel warp two pixel tiles (measured: cornell 450x300 974 vs 800 Mpaths/s; at 1920x1080 the megakernel wins)
+    // auto: the wavefront integrator when the scene has a BVH; the megakernel otherwise -- one lane per pixel when the frame gives
+    // every resident warp at least two pixel tiles, sample-parallel (a lane takes a chunk of a pixel's samples) for smaller frames
+    // such as the reference's default 450x300 (mod.rs:872-879)
     const bool has_bvh = ctx->ds.bvh_root != BVH_EMPTY_REF;
     const bool small_image = a.n_tiles < 2 * ctx->sm_count * (RENDER_MIN_BLOCKS * RENDER_THREADS / 32);
-    const bool wavefront = ctx->integrator == 2 || (ctx->integrator == 0 && (has_bvh || small_image));
+    const bool wavefront = ctx->integrator == 2 || (ctx->integrator == 0 && has_bvh);
+    const bool sample_parallel = !wavefront && (ctx->integrator == 3 || (ctx->integrator == 0 && small_image));
     // Work per launch.  The cancel flag is polled and progress published between launches only (the reference polls per pixel,
     // mod.rs:1003), so a caller that watches either gets launches of roughly 0.1-0.2 s: 2^28 samples on shared-memory scenes
     // (~2 Gpaths/s), 2^25 through a BVH; otherwise 2^31 samples per launch keep the launch count low.
@@ -639,6 +642,10 @@ int render_device_impl(ptb_ctx *ctx, int width, int height, uint64_t spp_begin, 
     uint64_t batch = std::max<uint64_t>(1, per_launch / npix);
     if (wavefront)  // whole wavefront batches: a launch smaller than the paths in flight would leave the queues short
         batch = std::max<uint64_t>(batch, std::max<uint64_t>(1, ctx->wf_opt.target_paths / npix));
+    if (sample_parallel) {  // the per-sample radiance buffer bounds a launch: 2^25 samples (512 MB)
+        batch = std::max<uint64_t>(1, std::min<uint64_t>(batch, (1ull << 25) / npix));
+        CU(ctx, ctx->sample_L.resize(std::min<uint64_t>(batch, spp_count) * npix));
+    }
     uint64_t done = 0;
     int rc = PTB_OK;
     double last_preview = now_ms();
@@ -651,9 +658,21 @@ int render_device_impl(ptb_ctx *ctx, int width, int height, uint64_t spp_begin, 
         if (wavefront) {
             CU(ctx, wavefront_render(ctx->ds, a, ctx->wf, ctx->sm_count, ctx->wf_opt, st, &ctx->stats.kernel_launches));
         } else {
+            a.sample_L = nullptr;
+            if (sample_parallel) {
+                // chunks of 8 samples, fewer when that would leave less than ~8 slots per resident lane
+                const uint64_t lanes = (uint64_t)ctx->sm_count * RENDER_MIN_BLOCKS * RENDER_THREADS;
+                uint64_t chunk = 8;
+                while (chunk > 1 && npix * ((n + chunk - 1) / chunk) < 8 * lanes) chunk /= 2;
+                a.sample_L = ctx->sample_L.p;
+                a.sp_chunk = (int)chunk;
+                a.sp_n_chunks = (int)((n + chunk - 1) / chunk);
+                if ((uint64_t)a.n_tiles * 32ull * (uint64_t)a.sp_n_chunks >= (1ull << 31))
+                    return fail(ctx, PTB_ERR_LIMIT, "ptb_render_device: too many sample chunks for one launch");
+            }
             CU(ctx, cudaMemsetAsync(ctx->tile_counter.p, 0, sizeof(int), st));
             CU(ctx, launch_render(ctx->ds, a, ctx->sm_count, st));
-            ctx->stats.kernel_launches++;
+            ctx->stats.kernel_launches += sample_parallel ? 2 : 1;
         }
         done += n;
         if (interactive) {

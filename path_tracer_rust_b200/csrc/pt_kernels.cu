@@ -10,6 +10,8 @@
 // "loose" part of the scene (few, large primitives: spheres, wall quads) is staged in shared memory
 // and scanned by all lanes in lock-step (broadcast LDS.128, no divergence); big meshes live in a
 // BVH (pt_bvh.cuh).  No tensor cores: there is no dense contraction in this workload.
+#include <algorithm>
+
 #include "pt_launch.h"
 #include "pt_scene_dev.cuh"
 
@@ -63,7 +65,11 @@ __global__ void __launch_bounds__(256) k_intersect(const DScene sc, const float 
 // ---------------------------------------------------------------------------------------------
 struct PathStackEntry { V3 o, d, T; int depth, code; };
 
-template <bool HAS_BVH>
+// SAMPLE_PARALLEL (frames with too few pixels to fill the GPU, e.g. the reference's default 450x300): a work slot is a chunk of
+// a.sp_chunk consecutive samples of one pixel instead of the whole pixel, so every lane of every SM has work; a finished sample's
+// radiance goes to a.sample_L[sample - spp_begin][pixel] and k_accumulate_samples adds them to the pixel in sample order
+// afterwards -- the same sequential fp32 sum (mod.rs:846), hence the same bits.
+template <bool HAS_BVH, bool SAMPLE_PARALLEL>
 __global__ void __launch_bounds__(RENDER_THREADS, RENDER_MIN_BLOCKS) k_render(const DScene sc, const RenderArgs a) {
     extern __shared__ float4 smem[];
     const float4 *s_obj, *s_tri;
@@ -77,9 +83,11 @@ __global__ void __launch_bounds__(RENDER_THREADS, RENDER_MIN_BLOCKS) k_render(co
     // lane by lane from one global counter.  A lane that has used up its pixel's sample budget stores the sum and takes the next
     // slot at once, so no lane waits for the slowest pixel of a tile.  One lane still owns one pixel at a time and walks its
     // samples in order: the per-pixel fp32 sum keeps the reference's order (mod.rs:846).
-    const unsigned n_slots = (unsigned)a.n_tiles * 32u;
+    const unsigned n_pixel_slots = (unsigned)a.n_tiles * 32u;
+    const unsigned n_slots = SAMPLE_PARALLEL ? n_pixel_slots * (unsigned)a.sp_n_chunks : n_pixel_slots;  // (< 2^31, checked by the host)
     const unsigned lt_mask = (1u << lane) - 1u;
-    const unsigned long long s_end = a.spp_begin + a.spp_count;
+    const unsigned long long s_last = a.spp_begin + a.spp_count;
+    unsigned long long s_end = s_last;  // SAMPLE_PARALLEL: end of the lane's current chunk
     bool have_pixel = false, retired = false;
     uint32_t pixel = 0;
     int px = 0, y = 0;
@@ -101,7 +109,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, RENDER_MIN_BLOCKS) k_render(co
     for (;;) {
         // a pixel whose samples are all done (no path in flight, no spare ray, budget used up) is written back
         if (have_pixel && !has_path && !spare_ok && s_next >= s_end) {
-            fb[0] = acc.x; fb[1] = acc.y; fb[2] = acc.z;
+            if (!SAMPLE_PARALLEL) { fb[0] = acc.x; fb[1] = acc.y; fb[2] = acc.z; }
             have_pixel = false;
         }
         const unsigned want_mask = __ballot_sync(0xffffffffu, !have_pixel && !retired);
@@ -111,9 +119,12 @@ __global__ void __launch_bounds__(RENDER_THREADS, RENDER_MIN_BLOCKS) k_render(co
             if (lane == leader) base = (unsigned)atomicAdd(a.tile_counter, __popc(want_mask));
             base = __shfl_sync(0xffffffffu, base, leader);
             if (!have_pixel && !retired) {
-                const unsigned slot = base + __popc(want_mask & lt_mask);
-                if (slot >= n_slots) retired = true;
+                const unsigned slot_all = base + __popc(want_mask & lt_mask);
+                if (slot_all >= n_slots) retired = true;
                 else {
+                    // chunk-major: the 32 lanes of a warp take the same chunk of 32 neighbouring pixels
+                    const unsigned chunk = SAMPLE_PARALLEL ? slot_all / n_pixel_slots : 0u;
+                    const unsigned slot = SAMPLE_PARALLEL ? slot_all % n_pixel_slots : slot_all;
                     const int tile = (int)(slot >> 5), pos = (int)(slot & 31u);
                     const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
                     px = tx * TILE_W + (pos & (TILE_W - 1));
@@ -121,9 +132,14 @@ __global__ void __launch_bounds__(RENDER_THREADS, RENDER_MIN_BLOCKS) k_render(co
                     if (px < W && row < H && a.spp_count > 0) {  // (off-image slots of edge tiles are simply skipped)
                         pixel = (uint32_t)row * (uint32_t)W + (uint32_t)px;
                         y = H - 1 - row;  // mod.rs:805
-                        fb = a.sum_rgb + 3ull * pixel;
-                        acc = a.fb_zero ? mk3(0.f, 0.f, 0.f) : mk3(fb[0], fb[1], fb[2]);
-                        s_next = a.spp_begin;
+                        if (SAMPLE_PARALLEL) {
+                            s_next = a.spp_begin + (unsigned long long)chunk * (unsigned)a.sp_chunk;
+                            s_end = s_next + (unsigned)a.sp_chunk < s_last ? s_next + (unsigned)a.sp_chunk : s_last;
+                        } else {
+                            fb = a.sum_rgb + 3ull * pixel;
+                            acc = a.fb_zero ? mk3(0.f, 0.f, 0.f) : mk3(fb[0], fb[1], fb[2]);
+                            s_next = a.spp_begin;
+                        }
                         have_pixel = true;
                     }
                 }
@@ -199,7 +215,9 @@ __global__ void __launch_bounds__(RENDER_THREADS, RENDER_MIN_BLOCKS) k_render(co
                         const V3 z = mk3(0.f, 0.f, 0.f);
                         L = ((Lc[0] + ((chain_mask & 2u) ? Lc[1] : z)) + ((chain_mask & 4u) ? Lc[2] : z)) + ((chain_mask & 8u) ? Lc[3] : z);
                     }
-                    acc = acc + L;
+                    if (SAMPLE_PARALLEL)
+                        a.sample_L[(size_t)(s - a.spp_begin) * ((size_t)W * (size_t)H) + pixel] = make_float4(L.x, L.y, L.z, 0.f);
+                    else acc = acc + L;
                     has_path = false;
                 }
             }
@@ -209,6 +227,21 @@ __global__ void __launch_bounds__(RENDER_THREADS, RENDER_MIN_BLOCKS) k_render(co
     // one atomic per warp
     for (int off = 16; off > 0; off >>= 1) n_segments += __shfl_down_sync(0xffffffffu, n_segments, off);
     if (lane == 0 && n_segments) atomicAdd(a.segment_counter, n_segments);
+}
+
+// radiance_v += radiance(sample) in sample order (mod.rs:846) for the K samples a SAMPLE_PARALLEL launch left in sample_L
+__global__ void __launch_bounds__(256) k_accumulate_samples(const float4 *__restrict__ sample_L, unsigned npix, unsigned K,
+                                                            float *__restrict__ sum_rgb, const int fb_zero) {
+    const unsigned stride = gridDim.x * blockDim.x;
+    for (unsigned pixel = blockIdx.x * blockDim.x + threadIdx.x; pixel < npix; pixel += stride) {
+        float *fb = sum_rgb + 3ull * pixel;
+        V3 acc = fb_zero ? mk3(0.f, 0.f, 0.f) : mk3(fb[0], fb[1], fb[2]);
+        for (unsigned k = 0; k < K; ++k) {
+            const float4 v = __ldcs(&sample_L[(size_t)k * npix + pixel]);
+            acc = acc + mk3(v.x, v.y, v.z);
+        }
+        fb[0] = acc.x; fb[1] = acc.y; fb[2] = acc.z;
+    }
 }
 
 // radiance / spp, clamp to [0,1] (mod.rs:849-856)
@@ -308,7 +341,8 @@ cudaError_t launch_intersect(const DScene &sc, const float *d_rays, unsigned lon
 cudaError_t launch_render(const DScene &sc, const RenderArgs &a, int sm_count, cudaStream_t st) {
     const size_t smem = loose_smem_bytes(sc);
     const bool bvh = sc.bvh_root != BVH_EMPTY_REF;
-    auto kern = bvh ? k_render<true> : k_render<false>;
+    const bool sp = a.sample_L != nullptr;
+    auto kern = sp ? (bvh ? k_render<true, true> : k_render<false, true>) : (bvh ? k_render<true, false> : k_render<false, false>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
@@ -317,10 +351,15 @@ cudaError_t launch_render(const DScene &sc, const RenderArgs &a, int sm_count, c
     if (per_sm < 1) return cudaErrorLaunchOutOfResources;
     // persistent grid: a whole number of resident CTAs per SM (148 SMs on B200)
     long long blocks = (long long)sm_count * per_sm;
-    const long long need = ((long long)a.n_tiles + RENDER_THREADS / 32 - 1) / (RENDER_THREADS / 32);
+    const long long need = ((long long)a.n_tiles * (sp ? a.sp_n_chunks : 1) + RENDER_THREADS / 32 - 1) / (RENDER_THREADS / 32);
     if (blocks > need) blocks = need;
     if (blocks < 1) blocks = 1;
     kern<<<(unsigned)blocks, RENDER_THREADS, smem, st>>>(sc, a);
+    if (sp) {  // the K = spp_count samples of every pixel, added in sample order
+        const unsigned npix = (unsigned)a.width * (unsigned)a.height;
+        const unsigned ablocks = (unsigned)std::max<long long>(1, std::min<long long>((npix + 255) / 256, (long long)sm_count * 8));
+        k_accumulate_samples<<<ablocks, 256, 0, st>>>(a.sample_L, npix, (unsigned)a.spp_count, a.sum_rgb, a.fb_zero);
+    }
     return cudaGetLastError();
 }
 

@@ -23,6 +23,10 @@ struct RenderArgs {
     int fb_zero;                           // 1: sum_rgb is to be treated as all zeros (first batch of a fresh frame: no load, no memset)
     int regen_batch;                       // lanes that must be waiting for a camera ray before the ray-gen code runs
     unsigned long long *segment_counter;   // [0] += closest-hit queries, [1] += BVH nodes fetched, [2] += BVH primitives tested
+    // sample-parallel megakernel (small frames): non-null = work slots are chunks of sp_chunk samples, per-sample radiance goes to
+    // sample_L[sample - spp_begin][pixel] and is added to sum_rgb in sample order by k_accumulate_samples (same launch call)
+    float4 *sample_L;
+    int sp_chunk, sp_n_chunks;
 };
 
 cudaError_t launch_rcp_selftest(unsigned long long *d_mismatches, int sm_count, cudaStream_t st);

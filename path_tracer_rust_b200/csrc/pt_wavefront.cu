@@ -224,7 +224,9 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_wf_trace(const DSce
 }
 
 // material arm of every queued segment; appends the next bounce
-__global__ void __launch_bounds__(256) k_wf_shade(const DScene sc, const WfQueue q, const int *__restrict__ ctr, WfQueue nq,
+// (four CTAs per SM: 64 registers with ~100 bytes of spills beat 92 registers at two CTAs -- mesh.json 1080p 996 -> 1164 Mpaths/s, the
+//  kernel waits on its queue loads and needs the warps; three CTAs: 1124)
+__global__ void __launch_bounds__(256, 4) k_wf_shade(const DScene sc, const WfQueue q, const int *__restrict__ ctr, WfQueue nq,
                                                   int *__restrict__ nctr, float4 *__restrict__ slots, int *__restrict__ branch_mask,
                                                   unsigned n_paths, unsigned npix, unsigned long long s0, unsigned long long seed,
                                                   unsigned long long *__restrict__ segment_counter) {

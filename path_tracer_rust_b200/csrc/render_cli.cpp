@@ -21,7 +21,7 @@ static const char *kSceneIds[] = {"cornell", "mesh", "single-sphere", "two-spher
 
 static void usage(const char *argv0) {
     std::fprintf(stderr,
-                 "Run with:\n  %s <samplesPerPixel = 100> <y-resolution = 300> <scene = 'mesh'> [--seed N] [--width W] [--gpu K] [--out FILE]\n\nScenes:",
+                 "Run with:\n  %s <samplesPerPixel = 100> <y-resolution = 300> <scene = 'mesh'> [--seed N] [--width W] [--gpu K | --gpus N] [--out FILE]\n\nScenes:",
                  argv0);
     for (size_t i = 0; i < sizeof kSceneIds / sizeof *kSceneIds; ++i) std::fprintf(stderr, " %zu: %s,", i, kSceneIds[i]);
     std::fprintf(stderr, " or a path to a scene .json\n");
@@ -30,7 +30,7 @@ static void usage(const char *argv0) {
 int main(int argc, char **argv) {
     // defaults of the GUI that is the reference's only caller: spp 100, res_y 300, scene "mesh" (main.rs:79,91-92)
     unsigned long long spp = 100, seed = 0;
-    int res_y = 300, width = 0, gpu = 0;
+    int res_y = 300, width = 0, gpu = 0, gpus = 1;  // --gpus N: devices 0..N-1 in one context (ptb_create_multi)
     std::string scene = "mesh", out_path;
     std::vector<std::string> pos;
     for (int i = 1; i < argc; ++i) {
@@ -39,6 +39,7 @@ int main(int argc, char **argv) {
         if (a == "--seed") seed = std::strtoull(next(), nullptr, 10);
         else if (a == "--width") width = std::atoi(next());
         else if (a == "--gpu") gpu = std::atoi(next());
+        else if (a == "--gpus") gpus = std::atoi(next());
         else if (a == "--out") out_path = next();
         else if (a == "-h" || a == "--help") { usage(argv[0]); return 0; }
         else pos.push_back(a);
@@ -64,10 +65,13 @@ int main(int argc, char **argv) {
     if (ptb_scene_load_json(json.c_str(), ".", &sc, err, sizeof err) != PTB_OK) { std::fprintf(stderr, "error: %s\n", err); return 1; }
     const ptb_scene_desc *desc = ptb_scene_get_desc(sc);
     ptb_ctx *ctx = nullptr;
-    if (ptb_create(gpu, &ctx) != PTB_OK) { std::fprintf(stderr, "error: %s\n", ptb_last_error(nullptr)); return 2; }
+    if (gpus < 1 || gpus > ptb_device_count()) { std::fprintf(stderr, "error: --gpus %d, but %d CUDA device(s) are visible\n", gpus, ptb_device_count()); return 2; }
+    std::vector<int> ids;
+    for (int g = 0; g < gpus; ++g) ids.push_back(gpus == 1 ? gpu : g);
+    if (ptb_create_multi(ids.data(), gpus, &ctx) != PTB_OK) { std::fprintf(stderr, "error: %s\n", ptb_last_error(nullptr)); return 2; }
     if (ptb_upload_scene(ctx, desc) != PTB_OK) { std::fprintf(stderr, "error: %s\n", ptb_last_error(ctx)); return 2; }
-    std::printf("Rendering scene %s (%llu objects), %llu samples per pixel, %dx%d resolution\n", ptb_scene_id(sc),
-                (unsigned long long)desc->n_objects, spp, width, res_y);
+    std::printf("Rendering scene %s (%llu objects), %llu samples per pixel, %dx%d resolution, %d GPU(s)\n", ptb_scene_id(sc),
+                (unsigned long long)desc->n_objects, spp, width, res_y, gpus);
     std::vector<float> img((size_t)width * res_y * 3);
     auto t0 = std::chrono::steady_clock::now();
     // progress line with elapsed / estimated total time, like the reference's print_progress (cmd_render.rs:54-80)

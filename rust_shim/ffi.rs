@@ -39,14 +39,24 @@ pub const PTB_CANCELLED: c_int = 1;
 pub const PTB_OUT_MEAN: c_int = 0;
 pub const PTB_OUT_SUM: c_int = 1;
 
+pub type ptb_preview_fn = Option<extern "C" fn(user: *mut c_void, mean_rgb: *const f32, width: c_int, height: c_int,
+                                               spp_done: u64, spp_total: u64)>;
+
 #[link(name = "ptb")]
 extern "C" {
+    pub fn ptb_device_count() -> c_int;
     pub fn ptb_create(device_id: c_int, out: *mut *mut ptb_ctx) -> c_int;
+    /// one context for several GPUs of the box (include/ptb.h: ptb_create_multi)
+    pub fn ptb_create_multi(device_ids: *const c_int, n_devices: c_int, out: *mut *mut ptb_ctx) -> c_int;
     pub fn ptb_destroy(ctx: *mut ptb_ctx);
     pub fn ptb_last_error(ctx: *const ptb_ctx) -> *const c_char;
     pub fn ptb_upload_scene(ctx: *mut ptb_ctx, desc: *const ptb_scene_desc) -> c_int;
     pub fn ptb_render(ctx: *mut ptb_ctx, width: c_int, height: c_int, spp_begin: u64, spp_count: u64, seed: u64, out_kind: c_int,
                       out_rgb: *mut f32, cancel: *const i32, samples_done: *mut u64) -> c_int;
+    /// ptb_render + RenderUpdate.image previews through `on_preview` (include/ptb.h: ptb_render_progressive)
+    pub fn ptb_render_progressive(ctx: *mut ptb_ctx, width: c_int, height: c_int, spp_begin: u64, spp_count: u64, seed: u64,
+                                  out_kind: c_int, out_rgb: *mut f32, cancel: *const i32, samples_done: *mut u64,
+                                  preview_interval_ms: f64, on_preview: ptb_preview_fn, user: *mut c_void) -> c_int;
     pub fn ptb_render_device(ctx: *mut ptb_ctx, width: c_int, height: c_int, spp_begin: u64, spp_count: u64, seed: u64,
                              d_sum_rgb: *mut f32, cuda_stream: *mut c_void, cancel: *const i32, samples_done: *mut u64) -> c_int;
     pub fn ptb_primary_hits(ctx: *mut ptb_ctx, width: c_int, height: c_int, obj: *mut i32, tri: *mut i32, t: *mut f32) -> c_int;

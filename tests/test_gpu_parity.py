@@ -98,7 +98,7 @@ def test_intersect_arbitrary_rays_bit_exact(be, sid):
 @pytest.mark.parametrize("sid,W,H,spp", [("cornell", 96, 64, 16), ("mesh", 60, 40, 4), ("single-sphere", 96, 64, 8),
                                          ("two-spheres", 96, 64, 8), ("three-spheres", 96, 64, 8), ("cartesian", 48, 32, 4),
                                          ("cornell", 37, 23, 5)])
-@pytest.mark.parametrize("integrator", [1, 2])          # 1 = megakernel, 2 = wavefront (auto would pick by image size)
+@pytest.mark.parametrize("integrator", [1, 2, 3])       # 1 = megakernel, 2 = wavefront, 3 = sample-parallel megakernel (auto picks by scene / size)
 def test_lockstep_framebuffer_bit_exact(be, sid, W, H, spp, integrator):
     import path_tracer_rust_b200.api as A
     be.set_option("integrator", integrator)
@@ -389,6 +389,38 @@ def test_wavefront_equals_megakernel_equals_oracle(sid, W, H, spp, paths):
         mk.close()
 
 
+def test_sample_parallel_megakernel_equals_oracle(be):
+    """Small frames: a lane takes a chunk of a pixel's samples and k_accumulate_samples adds the per-sample radiance in sample order
+    (mod.rs:846) -- same bits as one lane per pixel and as the oracle, for any chunking, sample offset and accumulation into a
+    non-empty framebuffer; and it is what `auto` picks for the reference's default 450x300 frame."""
+    import path_tracer_rust_b200 as P
+    import path_tracer_rust_b200.api as A
+    for sid, W, H, spp, begin in (("cornell", 45, 30, 37, 0), ("three-spheres", 64, 48, 20, 5), ("cornell", 450, 300, 12, (1 << 32) + 3)):
+        sc, osc = load_both(be, sid)
+        o, ost = osc.render_sum(W, H, spp, spp_begin=begin, seed=8)
+        for integ in (3, 0):
+            be.set_option("integrator", integ)
+            g = be.render(W, H, spp, spp_begin=begin, seed=8, out_kind=A.PTB_OUT_SUM)
+            st = be.stats()
+            assert st["segments"] == int(ost[0]) and st["kernel_launches"] == 2, (sid, integ, st["kernel_launches"])
+            assert np.array_equal(bits(g), bits(o)), (sid, integ)
+    # accumulate into a framebuffer that already holds samples (checkpoint / resume path)
+    be.set_option("integrator", 3)
+    W, H = 45, 30
+    sc, osc = load_both(be, "cornell")
+    fb = be.device_alloc(W * H * 12)
+    try:
+        be.device_memset(fb, 0, W * H * 12)
+        be.render_device(W, H, 9, fb, spp_begin=0, seed=8, sync=True)
+        be.render_device(W, H, 28, fb, spp_begin=9, seed=8, sync=True)
+        got = np.empty((W * H, 3), f32)
+        be.device_to_host(got, fb)
+        assert np.array_equal(bits(got), bits(osc.render_sum(W, H, 37, seed=8)[0]))
+    finally:
+        be.device_free(fb)
+        be.set_option("integrator", 0)
+
+
 def test_render_cli_writes_reference_ppm(tmp_path):
     """The resurrected `render <spp> <res_y> <scene>` command (cmd_render.rs:17-44): its PPM must equal, byte for byte, the PPM the
     oracle writes for the same seed (P3, two comment lines, reversed pixel order, gamma 2.2 -> u8; mod.rs:1042-1076)."""
@@ -452,7 +484,7 @@ def test_checkpoint_resume_is_bit_identical(be):
     import path_tracer_rust_b200 as P
     import path_tracer_rust_b200.api as A
     W, H = 80, 52
-    for sid, integ in (("cornell", 1), ("cornell", 2), ("mesh", 0)):
+    for sid, integ in (("cornell", 1), ("cornell", 2), ("cornell", 3), ("mesh", 0), ("mesh", 3)):
         be.set_option("integrator", integ)
         be.upload_scene(P.Scene.load(sid))
         full = be.render(W, H, 11, seed=6, out_kind=A.PTB_OUT_SUM)
@@ -479,7 +511,7 @@ def test_edge_cases(be, kat_scene):
     # empty scene: every ray misses, the image is black, one segment per sample
     path = kat_scene([], "empty")
     sc, osc = load_both(be, path)
-    for integ in (1, 2):
+    for integ in (1, 2, 3):
         be.set_option("integrator", integ)
         be.upload_scene(sc)
         img = be.render(17, 9, 3, seed=1, out_kind=A.PTB_OUT_SUM)
@@ -491,8 +523,8 @@ def test_edge_cases(be, kat_scene):
     assert not ofb.any() and int(ost[0]) == 17 * 9 * 3
     # one pixel, one sample; zero rays; zero samples in SUM mode; widths that are not multiples of the 8x4 tile
     sc, osc = load_both(be, "cornell")
-    for (W, H, spp) in ((1, 1, 1), (1, 7, 2), (9, 1, 3), (33, 5, 1)):
-        for integ in (1, 2):
+    for (W, H, spp) in ((1, 1, 1), (1, 7, 2), (9, 1, 3), (33, 5, 1), (33, 5, 21)):
+        for integ in (1, 2, 3):
             be.set_option("integrator", integ)
             g = be.render(W, H, spp, seed=2, out_kind=A.PTB_OUT_SUM)
             o, _ = osc.render_sum(W, H, spp, seed=2)

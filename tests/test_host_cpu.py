@@ -114,6 +114,41 @@ def test_siphash13_pixel_hash(P):
     assert A.hash_pixels(np.zeros((0, 3), f32)) == 15130871412783076140
     a = np.arange(30, dtype=f32).reshape(10, 3)
     assert A.hash_pixels(a) != A.hash_pixels(a[::-1].copy())
+    # Second pin, from the SipHash specification itself (Aumasson & Bernstein 2012): a straight restatement of SipHash-c-d that
+    # reproduces the paper's SipHash-2-4 test vector (key 00..0f, message 00..0e -> a129ca6149be45e5) is run as SipHash-1-3 with the
+    # zero key over the little-endian u32 bit patterns of the pixels -- what hash_vec_of_vectors feeds DefaultHasher (mod.rs:916-926).
+    M = (1 << 64) - 1
+    rotl = lambda x, b: ((x << b) | (x >> (64 - b))) & M
+
+    def siphash(c, d, k0, k1, msg: bytes) -> int:
+        v0, v1, v2, v3 = k0 ^ 0x736f6d6570736575, k1 ^ 0x646f72616e646f6d, k0 ^ 0x6c7967656e657261, k1 ^ 0x7465646279746573
+
+        def rnd(v0, v1, v2, v3):
+            v0 = (v0 + v1) & M; v1 = rotl(v1, 13) ^ v0; v0 = rotl(v0, 32)
+            v2 = (v2 + v3) & M; v3 = rotl(v3, 16) ^ v2
+            v0 = (v0 + v3) & M; v3 = rotl(v3, 21) ^ v0
+            v2 = (v2 + v1) & M; v1 = rotl(v1, 17) ^ v2; v2 = rotl(v2, 32)
+            return v0, v1, v2, v3
+
+        tail = len(msg) % 8
+        words = [int.from_bytes(msg[i:i + 8], "little") for i in range(0, len(msg) - tail, 8)]
+        words.append(int.from_bytes(msg[len(msg) - tail:], "little") | ((len(msg) & 0xff) << 56))
+        for m in words:
+            v3 ^= m
+            for _ in range(c):
+                v0, v1, v2, v3 = rnd(v0, v1, v2, v3)
+            v0 ^= m
+        v2 ^= 0xff
+        for _ in range(d):
+            v0, v1, v2, v3 = rnd(v0, v1, v2, v3)
+        return v0 ^ v1 ^ v2 ^ v3
+
+    key = bytes(range(16))
+    assert siphash(2, 4, int.from_bytes(key[:8], "little"), int.from_bytes(key[8:], "little"), bytes(range(15))) == 0xa129ca6149be45e5
+    assert siphash(1, 3, 0, 0, b"") == 15130871412783076140
+    for px in (a, np.array([[0.25, 1.0, 0.0]], f32), np.linspace(0, 1, 3 * 7, dtype=f32).reshape(7, 3)):   # 120, 12, 84 bytes
+        assert A.hash_pixels(px) == siphash(1, 3, 0, 0, np.ascontiguousarray(px).view(np.uint32).astype("<u4").tobytes()), px.shape
+    assert A.hash_pixels(np.array([[0.25, 1.0, 0.0]], f32)) == 0x86fc3ab182d6bc44   # the one pixel (0.25, 1, 0)
 
 
 def test_shard_samples_partition():

@@ -18,7 +18,12 @@ be = P.Backend(0)
 for kv in os.environ.get('PTB_OPTS', '').split(','):
     if '=' in kv:
         be.set_option(kv.split('=')[0], float(kv.split('=')[1]))
-be.upload_scene(P.Scene.load(scene))
+if scene == "synthetic":   # the BASELINE C5 scene (1.31 M triangles + 10 k spheres), generated like bench.py does
+    import bench
+    path, base = bench.resolve_scene("synthetic")
+    be.upload_scene(P.Scene.load(path, base_dir=base))
+else:
+    be.upload_scene(P.Scene.load(scene))
 for i in range(reps):
     t0 = time.perf_counter()
     be.render(W, H, spp, seed=i, out_kind=A.PTB_OUT_SUM)

@@ -234,8 +234,10 @@ def main():
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        cpu_group = dist.new_group(backend="gloo")   # host-side waits: an NCCL barrier would spin a kernel on the waiting ranks' GPUs
     else:
         dist = None
+        cpu_group = None
 
     be = P.Backend(local_rank)
     for kv in args.opt:
@@ -473,7 +475,9 @@ def main():
                 mb.close()
             except Exception as exc:  # noqa: BLE001
                 cabi = {"error": f"{type(exc).__name__}: {exc}"}
-        barrier()
+        # the other ranks wait on the HOST (gloo): a pending NCCL barrier is a kernel spinning on their GPU, and two processes on one
+        # GPU are time-sliced -- it would halve the speed of the devices rank 0 is driving (measured)
+        dist.barrier(group=cpu_group)
 
     if rank == 0:
         line["extra_workloads"] = extra_lines

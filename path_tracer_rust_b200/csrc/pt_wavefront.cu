@@ -93,16 +93,16 @@ __global__ void __launch_bounds__(256) k_wf_generate(const DScene sc, int W, int
             const float r2 = 2.0f * u32_to_unit(rnd[1]);
             camera_ray(sc, W, H, px, H - 1 - row, xsub, ysub, tent(r1), tent(r2), o, d);
             front = loose_hit(sc, s_obj, o, d, amask, best);
-            branch_mask[p] = 0;
+            __stcs(&branch_mask[p], 0);
         }
         int j, unused;
         append2(sc, q, ctr, valid, front, false, false, lt_mask, j, unused);
-        if (j >= 0) {
-            q.o[j] = make_float4(o.x, o.y, o.z, __int_as_float((int)p));
-            q.d[j] = make_float4(d.x, d.y, d.z, __int_as_float(0));
-            q.T[j] = make_float4(1.f, 1.f, 1.f, 0.f);
-            q.L[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            q.hit_t[j] = best.t; q.hit_ref[j] = best.ref; q.hit_prio[j] = best.prio;
+        if (j >= 0) {  // streaming stores: queue data is written once and read once, it must not push the BVH out of the L2
+            __stcs(&q.o[j], make_float4(o.x, o.y, o.z, __int_as_float((int)p)));
+            __stcs(&q.d[j], make_float4(d.x, d.y, d.z, __int_as_float(0)));
+            __stcs(&q.T[j], make_float4(1.f, 1.f, 1.f, 0.f));
+            __stcs(&q.L[j], make_float4(0.f, 0.f, 0.f, 0.f));
+            __stcs(&q.hit_t[j], best.t); __stcs(&q.hit_ref[j], best.ref); __stcs(&q.hit_prio[j], best.prio);
         }
     }
 }
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(256, 4) k_wf_shade(const DScene sc, const WfQu
                 }
             }
             if (!cont && PTB_CHECKED((unsigned)path < n_paths && (unsigned)code < 4u, PTB_CHK_SLOT, sc.check))
-                slots[(size_t)code * n_paths + (size_t)path] = make_float4(L.x, L.y, L.z, 0.f);  // branch finished
+                __stcs(&slots[(size_t)code * n_paths + (size_t)path], make_float4(L.x, L.y, L.z, 0.f));  // branch finished
         }
         // closest hit of the new segments over the shared-memory list (so the trace kernel only does BVH work), then one atomic
         // per warp for everything the warp appends
@@ -297,13 +297,13 @@ __global__ void __launch_bounds__(256, 4) k_wf_shade(const DScene sc, const WfQu
         if (m2 != 0u && n_out == 2) f2 = loose_hit(sc, s_obj, mk3(k_o.x, k_o.y, k_o.z), mk3(k_d.x, k_d.y, k_d.z), m2, h2);
         int j1, j2;
         append2(sc, nq, nctr, n_out >= 1, f1, n_out == 2, f2, lt_mask, j1, j2);
-        if (j1 >= 0) {
-            nq.o[j1] = c_o; nq.d[j1] = c_d; nq.T[j1] = c_T; nq.L[j1] = c_L;
-            nq.hit_t[j1] = h1.t; nq.hit_ref[j1] = h1.ref; nq.hit_prio[j1] = h1.prio;
+        if (j1 >= 0) {  // (streaming stores, like every queue access: the L2 is for the BVH)
+            __stcs(&nq.o[j1], c_o); __stcs(&nq.d[j1], c_d); __stcs(&nq.T[j1], c_T); __stcs(&nq.L[j1], c_L);
+            __stcs(&nq.hit_t[j1], h1.t); __stcs(&nq.hit_ref[j1], h1.ref); __stcs(&nq.hit_prio[j1], h1.prio);
         }
         if (j2 >= 0) {
-            nq.o[j2] = k_o; nq.d[j2] = k_d; nq.T[j2] = k_T; nq.L[j2] = make_float4(0.f, 0.f, 0.f, 0.f);
-            nq.hit_t[j2] = h2.t; nq.hit_ref[j2] = h2.ref; nq.hit_prio[j2] = h2.prio;
+            __stcs(&nq.o[j2], k_o); __stcs(&nq.d[j2], k_d); __stcs(&nq.T[j2], k_T); __stcs(&nq.L[j2], make_float4(0.f, 0.f, 0.f, 0.f));
+            __stcs(&nq.hit_t[j2], h2.t); __stcs(&nq.hit_ref[j2], h2.ref); __stcs(&nq.hit_prio[j2], h2.prio);
         }
     }
 }

@@ -266,6 +266,108 @@ __global__ void __launch_bounds__(256) k_top_levels(const float4 *__restrict__ n
     if (threadIdx.x == 0) *n_top = min(s_total, cap);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Binary hierarchy by binned SAH on the host, for small primitive sets (a few thousand: scenes/mesh.json has 810 triangles).
+// Same output convention as k_hierarchy (Karras): n - 1 internal nodes, node 0 is the root, child ref >= 0 = internal node,
+// < 0 = ~leaf index, a node covers the leaves [first, last] of the order `idx`; the device pipeline (refit, collapse to
+// four-wide nodes) is the same for both builders.  Only the TOPOLOGY comes from here -- boxes are refitted on the device from
+// the padded primitive boxes -- so nothing about the result depends on it, only how many nodes and primitives a ray visits
+// (measured on mesh.json 1080p: see DESIGN.md section 4).
+// ---------------------------------------------------------------------------------------------
+struct HostBox { float lo[3], hi[3]; };
+struct SahOut { std::vector<int> idx, left, right, first, last, parent_inner, parent_leaf; };
+
+void sah_hierarchy(const std::vector<HostBox> &box, SahOut &o) {
+    const int n = (int)box.size();
+    o.idx.resize(n);
+    for (int i = 0; i < n; ++i) o.idx[i] = i;
+    const int ni = std::max(n - 1, 1);
+    o.left.assign(ni, 0); o.right.assign(ni, 0); o.first.assign(ni, 0); o.last.assign(ni, 0);
+    o.parent_inner.assign(std::max(n, 1), -1); o.parent_leaf.assign(std::max(n, 1), -1);
+    if (n < 2) return;
+    auto area = [](const float *lo, const float *hi) {
+        const double dx = std::max(0.f, hi[0] - lo[0]), dy = std::max(0.f, hi[1] - lo[1]), dz = std::max(0.f, hi[2] - lo[2]);
+        return dx * dy + dy * dz + dz * dx;
+    };
+    struct Job { int node, begin, end, depth; };
+    std::vector<Job> jobs;
+    jobs.push_back({0, 0, n, 0});
+    int next_node = 1;
+    constexpr int NB = 16;
+    while (!jobs.empty()) {
+        const Job j = jobs.back();
+        jobs.pop_back();
+        const int cnt = j.end - j.begin;
+        o.first[j.node] = j.begin; o.last[j.node] = j.end - 1;
+        float clo[3] = {3e38f, 3e38f, 3e38f}, chi[3] = {-3e38f, -3e38f, -3e38f};
+        for (int k = j.begin; k < j.end; ++k) {
+            const HostBox &b = box[o.idx[k]];
+            for (int a = 0; a < 3; ++a) { const float c = 0.5f * (b.lo[a] + b.hi[a]); clo[a] = std::min(clo[a], c); chi[a] = std::max(chi[a], c); }
+        }
+        int best_axis = -1, best_bin = 0;
+        double best_cost = 1e300;
+        for (int a = 0; a < 3; ++a) {
+            const float ext = chi[a] - clo[a];
+            if (!(ext > 0.f)) continue;
+            int bc[NB] = {0};
+            float blo[NB][3], bhi[NB][3];
+            for (int q = 0; q < NB; ++q) for (int c = 0; c < 3; ++c) { blo[q][c] = 3e38f; bhi[q][c] = -3e38f; }
+            const float scale = NB / ext;
+            for (int k = j.begin; k < j.end; ++k) {
+                const HostBox &b = box[o.idx[k]];
+                const int q = std::min(NB - 1, std::max(0, (int)((0.5f * (b.lo[a] + b.hi[a]) - clo[a]) * scale)));
+                bc[q]++;
+                for (int c = 0; c < 3; ++c) { blo[q][c] = std::min(blo[q][c], b.lo[c]); bhi[q][c] = std::max(bhi[q][c], b.hi[c]); }
+            }
+            double la[NB], ra[NB];
+            int lc[NB], rc[NB];
+            float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
+            int c0 = 0;
+            for (int q = 0; q < NB; ++q) {
+                c0 += bc[q];
+                for (int c = 0; c < 3; ++c) { lo[c] = std::min(lo[c], blo[q][c]); hi[c] = std::max(hi[c], bhi[q][c]); }
+                lc[q] = c0; la[q] = c0 ? area(lo, hi) : 0.0;
+            }
+            for (int c = 0; c < 3; ++c) { lo[c] = 3e38f; hi[c] = -3e38f; }
+            c0 = 0;
+            for (int q = NB - 1; q >= 0; --q) {
+                c0 += bc[q];
+                for (int c = 0; c < 3; ++c) { lo[c] = std::min(lo[c], blo[q][c]); hi[c] = std::max(hi[c], bhi[q][c]); }
+                rc[q] = c0; ra[q] = c0 ? area(lo, hi) : 0.0;
+            }
+            for (int q = 0; q + 1 < NB; ++q) {  // split between bin q and q + 1
+                if (lc[q] == 0 || rc[q + 1] == 0) continue;
+                const double cost = la[q] * lc[q] + ra[q + 1] * rc[q + 1];
+                if (cost < best_cost) { best_cost = cost; best_axis = a; best_bin = q; }
+            }
+        }
+        int mid;
+        // all centroids coincide: split the list in the middle; likewise below depth 40, so that the tree stays within the traversal
+        // stack whatever the input (40 + log2(16384) binary levels at most)
+        if (best_axis < 0 || j.depth >= 40) mid = j.begin + cnt / 2;
+        else {
+            const float ext = chi[best_axis] - clo[best_axis], scale = NB / ext;
+            auto it = std::partition(o.idx.begin() + j.begin, o.idx.begin() + j.end, [&](int p) {
+                const HostBox &b = box[p];
+                const int q = std::min(NB - 1, std::max(0, (int)((0.5f * (b.lo[best_axis] + b.hi[best_axis]) - clo[best_axis]) * scale)));
+                return q <= best_bin;
+            });
+            mid = (int)(it - o.idx.begin());
+            if (mid == j.begin || mid == j.end) mid = j.begin + cnt / 2;
+        }
+        auto child = [&](int b, int e) {
+            if (e - b == 1) { o.parent_leaf[b] = j.node; return ~b; }
+            const int id = next_node++;
+            o.parent_inner[id] = j.node;
+            jobs.push_back({id, b, e, j.depth + 1});
+            return id;
+        };
+        o.left[j.node] = child(j.begin, mid);
+        o.right[j.node] = child(mid, j.end);
+    }
+    o.parent_inner[0] = -1;
+}
+
 template <typename T>
 cudaError_t dev_alloc(T **p, size_t n) { return cudaMalloc(reinterpret_cast<void **>(p), std::max<size_t>(n, 1) * sizeof(T)); }
 
@@ -436,7 +538,39 @@ cudaError_t bvh_build(const ptb_scene_desc &desc, const std::vector<char> &in_bv
 
     k_prim_boxes<<<B, T, 0, st>>>(d_recs, d_pads, n, d_blo, d_bhi);
     BV(cudaGetLastError());
-    if (n > 1) {
+    if (n > 1 && n <= opt.sah_max_prims) {
+        // small set: binned-SAH topology from the host (boxes here are the unpadded ones, good enough to choose splits)
+        std::vector<HostBox> hb((size_t)n);
+        for (int i = 0; i < n; ++i) {
+            const float4 A = recs[3 * (size_t)i], E1 = recs[3 * (size_t)i + 1], E2 = recs[3 * (size_t)i + 2];
+            int32_t tag;
+            std::memcpy(&tag, &E1.w, 4);
+            const float a[3] = {A.x, A.y, A.z};
+            if (tag < 0) {
+                const float r = std::sqrt(E1.x);
+                for (int c = 0; c < 3; ++c) { hb[i].lo[c] = a[c] - r; hb[i].hi[c] = a[c] + r; }
+            } else {
+                const float e1[3] = {E1.x, E1.y, E1.z}, e2[3] = {E2.x, E2.y, E2.z};
+                for (int c = 0; c < 3; ++c) {
+                    hb[i].lo[c] = std::min(a[c], std::min(a[c] + e1[c], a[c] + e2[c]));
+                    hb[i].hi[c] = std::max(a[c], std::max(a[c] + e1[c], a[c] + e2[c]));
+                }
+            }
+        }
+        SahOut so;
+        sah_hierarchy(hb, so);
+        const size_t bi = sizeof(int) * (size_t)n_inner, bl = sizeof(int) * (size_t)n;
+        BV(cudaMemcpyAsync(d_idx2, so.idx.data(), bl, cudaMemcpyHostToDevice, st));
+        BV(cudaMemcpyAsync(d_left, so.left.data(), bi, cudaMemcpyHostToDevice, st));
+        BV(cudaMemcpyAsync(d_right, so.right.data(), bi, cudaMemcpyHostToDevice, st));
+        BV(cudaMemcpyAsync(d_first, so.first.data(), bi, cudaMemcpyHostToDevice, st));
+        BV(cudaMemcpyAsync(d_last, so.last.data(), bi, cudaMemcpyHostToDevice, st));
+        BV(cudaMemcpyAsync(d_pin, so.parent_inner.data(), bl, cudaMemcpyHostToDevice, st));
+        BV(cudaMemcpyAsync(d_pleaf, so.parent_leaf.data(), bl, cudaMemcpyHostToDevice, st));
+        BV(cudaStreamSynchronize(st));  // (the host vectors go out of scope)
+        BV(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_alive, d_new, n_inner, st));
+        BV(cudaMalloc(&d_tmp, std::max<size_t>(tmp_bytes, 16)));
+    } else if (n > 1) {
         float3 cmin = make_float3((float)cl[0], (float)cl[1], (float)cl[2]);
         auto sc = [&](int k) { const double e = ch[k] - cl[k]; return (float)(e > 0 ? 2097151.0 / e : 0.0); };
         float3 cscale = make_float3(sc(0), sc(1), sc(2));
@@ -449,11 +583,13 @@ cudaError_t bvh_build(const ptb_scene_desc &desc, const std::vector<char> &in_bv
         BV(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys2, d_idx, d_idx2, n, 0, 63, st));
         k_hierarchy<<<(n_inner + T - 1) / T, T, 0, st>>>(d_keys2, n, d_left, d_right, d_first, d_last, d_pin, d_pleaf);
         BV(cudaGetLastError());
+    }
+    if (n > 1) {
         BV(cudaMemsetAsync(d_flags, 0, sizeof(int) * (size_t)n, st));
         BV(cudaMemsetAsync(d_depth, 0, sizeof(int), st));
         k_refit<<<B, T, 0, st>>>(d_idx2, d_blo, d_bhi, n, d_left, d_right, d_pin, d_pleaf, d_flags, d_nlo, d_nhi, d_depth);
         BV(cudaGetLastError());
-        k_alive<<<(n_inner + T - 1) / T, T, 0, st>>>(d_first, d_last, n_inner, std::min(8, std::max(1, opt.leaf_max)), d_alive);
+        k_alive<<<(n_inner + T - 1) / T, T, 0, st>>>(d_first, d_last, n_inner, std::min(8, std::max(1, n <= opt.sah_max_prims ? opt.leaf_max_small : opt.leaf_max)), d_alive);
         BV(cudaGetLastError());
         k_select4<<<(n_inner + T - 1) / T, T, 0, st>>>(n_inner, d_alive, d_pin, d_sel);
         BV(cudaGetLastError());

@@ -25,7 +25,9 @@ struct BvhDevice {
 struct BvhOptions {
     double min_tris = 24;     // meshes with fewer triangles stay in the lock-step shared-memory list
     double min_spheres = 48;  // scenes with fewer spheres keep them in the shared-memory list
-    int leaf_max = 2;         // primitives per leaf after collapsing small subtrees (1..8); measured best on B200
+    int leaf_max = 2;         // primitives per leaf after collapsing small subtrees (1..8); measured best on B200 for the 1.3 M-triangle scene
+    int leaf_max_small = 4;   // the same for sets that take the host SAH path (mesh.json, 810 triangles: 4 -> +2 % over 2)
+    int sah_max_prims = 16384; // sets up to this size get a binned-SAH topology from the host, larger ones the device LBVH (Karras)
     int top_levels = 5;       // four-wide levels copied for the trace kernel's shared memory (0..5); measured on B200: 0 -> 4 levels +6 %, 5 levels (512-thread CTAs) +11 %
 #ifdef PTB_EXPERIMENTS
     double pad_scale = 1.0;   // scales the conservative box padding; anything below 1 voids the parity guarantee

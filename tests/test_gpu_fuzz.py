@@ -93,6 +93,8 @@ def test_random_scene_matches_oracle(tmp_path, idx, n_spheres, n_inline, n_file_
     for opts in ({"integrator": 1}, {"integrator": 2, "wavefront_paths": 5000},
                  {"integrator": 1, "bvh_min_tris": 1e18, "bvh_min_spheres": 1e18}, {"integrator": 2, "bvh_min_tris": 2, "bvh_min_spheres": 2},
                  {"integrator": 2, "bvh_leaf_max": 4, "bvh_min_tris": 2, "bvh_min_spheres": 2},
+                 {"integrator": 2, "bvh_sah_max_prims": 0, "bvh_min_tris": 2, "bvh_min_spheres": 2},   # device LBVH instead of the host SAH topology
+                 {"integrator": 1, "bvh_sah_max_prims": 0, "bvh_leaf_max": 3, "bvh_min_tris": 2, "bvh_min_spheres": 2},
                  {"integrator": 2, "wf_refill": 1, "wf_descend_min": 30, "bvh_top_levels": 2, "bvh_min_tris": 2, "bvh_min_spheres": 2,
                   "wavefront_paths": 7000},
                  {"integrator": 1, "quad_min_ratio": 0.0},      # every one-pair mesh takes the vote-free path, failing gates included

@@ -176,13 +176,15 @@ __global__ void __launch_bounds__(RENDER_THREADS, RENDER_MIN_BLOCKS) k_render(co
         }
         // ---- one radiance() call (mod.rs:662): event (code<<4 | new_depth); slots 0 = RR, 1,2 = diffuse, 3 = refraction.
         // The whole warp walks the object stream (lanes without a path are passengers: full-mask votes, no divergence).
-        uint32_t rnd[4];
-        philox4x32_10(pixel, (uint32_t)s, (uint32_t)(s >> 32), ((uint32_t)code << 4) | (uint32_t)(depth + 1), a.rk, rnd);
         const Hit h = closest_hit<HAS_BVH>(sc, s_obj, o, d, 0xffffffffu, has_path);
         if (has_path) {
             nseg++;
             bool cont = false;
             if (h.ref != REF_NONE) {
+                // the event's random numbers are only needed once something is hit (an open scene's rays mostly leave: the
+                // sphere scenes spend 13 % of their instructions here otherwise)
+                uint32_t rnd[4];
+                philox4x32_10(pixel, (uint32_t)s, (uint32_t)(s >> 32), ((uint32_t)code << 4) | (uint32_t)(depth + 1), a.rk, rnd);
                 int obj, tri;
                 V3 x, n;
                 finish_hit(sc, s_obj, s_tri, h, o, d, obj, tri, x, n);

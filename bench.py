@@ -239,7 +239,12 @@ def main():
         dist = None
         cpu_group = None
 
-    be = P.Backend(local_rank)
+    # `python bench.py --gpus N` WITHOUT torchrun (one process): all N GPUs through one multi-GPU context (ptb_create_multi)
+    single_process_multi = world == 1 and args.gpus > 1
+    if single_process_multi and torch.cuda.device_count() < args.gpus:
+        raise SystemExit(f"bench.py: --gpus {args.gpus} but only {torch.cuda.device_count()} CUDA device(s) are visible")
+    n_gpus = args.gpus if single_process_multi else world
+    be = P.Backend(list(range(args.gpus))) if single_process_multi else P.Backend(local_rank)
     for kv in args.opt:
         name, _, value = kv.partition("=")
         be.set_option(name, float(value))
@@ -279,19 +284,22 @@ def main():
             if int(flag.item()) == 0:
                 frame = None
                 use_peer = False
-        shard = CudaShardRenderer(be, W, H, seed=2026, device=dev) if not use_peer else None
+        shard = CudaShardRenderer(be, W, H, seed=2026, device=dev) if not (use_peer or single_process_multi) else None
         nfl = W * H * 3
         host_img = torch.empty(nfl, dtype=torch.float32).pin_memory() if rank == 0 else None
         host_np = host_img.numpy().reshape(-1, 3) if rank == 0 else None
 
         def step_resident(n_spp):
+            if single_process_multi:   # the multi-GPU context renders, reduces over peer memory and copies to the host in one call
+                be.render(W, H, n_spp, seed=2026, out=host_np)
+                return None
             if use_peer:
                 return frame.render(n_spp, to_host=False)
             return render_sharded(shard, n_spp, rank, world)
 
         def step_e2e():
             be.upload_scene(scene)                       # H2D of the scene (flatten + upload + device BVH build)
-            if world == 1:
+            if world == 1:   # (also the single-process multi-GPU context)
                 # the reference-facing call itself: ptb_render() with a HOST output buffer (here pinned), blocking like render()
                 be.render(W, H, spp, seed=2026, out=host_np)
                 return
@@ -320,7 +328,7 @@ def main():
             times.append(e0.elapsed_time(e1))
             st = be.stats()
             seg_total += st["segments"]
-            launches += st["kernel_launches"] + (1 if (rank == 0 or use_peer) else 0)
+            launches += st["kernel_launches"] + (1 if ((rank == 0 or use_peer) and not single_process_multi) else 0)
         barrier()
         clocks = sampler.stop()
         st_last = be.stats()
@@ -354,9 +362,9 @@ def main():
         sd = scene._desc.contents
         scene_bytes = int(sd.n_objects) * 80 + int(sd.n_triangles) * 36 + 36
         cpu = None
-        if cpu_mode == "sample" and world == 1:
+        if cpu_mode == "sample" and n_gpus == 1:
             cpu = cpu_reference_run(scene_id, W, H, 12.0)
-        elif cpu_mode == "frame" and world == 1:
+        elif cpu_mode == "frame" and n_gpus == 1:
             cpu = cpu_full_frame(scene_id, W, H, spp)
         # roofline of the dominant kernel: FP32 issue slots.  Algorithmic flops per segment follow SURVEY.md 8d:
         # 17 per sphere/gate test + 45 per triangle test + 30 per four-wide BVH node + 120 shading, with the reference algorithm's
@@ -380,11 +388,11 @@ def main():
         hbm = None
         if tps["bvh_nodes"] > 0:
             bytes_per_seg = 76.0 + 44.0 + 72.0 + 8.0
-            gbs = seg_total / max(world, 1) / steps * bytes_per_seg / (kernel_ms_last * 1e-3) * 1e-9 if kernel_ms_last > 0 else None
+            gbs = seg_total / max(n_gpus, 1) / steps * bytes_per_seg / (kernel_ms_last * 1e-3) * 1e-9 if kernel_ms_last > 0 else None
             hbm = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"] if gbs else None,
                    "bytes_per_segment": bytes_per_seg,
                    "note": "queue traffic only (algorithmic bytes per ray segment); BVH nodes / primitives are served from L2"}
-        seg_per_gpu = seg_total / max(world, 1) / steps
+        seg_per_gpu = seg_total / max(n_gpus, 1) / steps
         kern_s = kernel_ms_last * 1e-3
         achieved = seg_per_gpu * flops_per_seg / kern_s * 1e-12 if kern_s > 0 else None
         traffic, ncu_note = None, None
@@ -394,14 +402,16 @@ def main():
             if tj:
                 traffic, ncu_note = tj["dram_bytes_per_launch"], {k: tj[k] for k in ("kernel", "launch", "algorithmic_bytes_per_launch", "ncu", "source")}
         return {
-            "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": n_gpus, "steps": steps, "warmup": warmup,
             "ms_per_step": total_ms / max(steps, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{workload}: scenes/{scene_id}.json {W}x{H} x {spp} spp, spp sharded over {world} GPU(s), "
-                                   + ("fused peer-memory reduce+resolve kernel over NVLink (CUDA IPC)" if use_peer
-                                      else ("NCCL fp32 sum-reduce" if world > 1 else "no reduce step")), "scene": scene_id, "width": W, "height": H, "spp": spp,
+            "config": {"workload": f"{workload}: scenes/{scene_id}.json {W}x{H} x {spp} spp, spp sharded over {n_gpus} GPU(s), "
+                                   + ("one process, ptb_create_multi: fused peer-memory reduce+resolve kernel over NVLink, image copied to the host "
+                                      "inside every timed step" if single_process_multi else
+                                      ("fused peer-memory reduce+resolve kernel over NVLink (CUDA IPC)" if use_peer
+                                       else ("NCCL fp32 sum-reduce" if world > 1 else "no reduce step"))), "scene": scene_id, "width": W, "height": H, "spp": spp,
                        "spp_reduced_for_development": reduced, "l2": "flushed between steps (256 MiB device write)",
-                       "parallelism": f"spp-shard x{world}", "backend_options": list(args.opt),
+                       "parallelism": f"spp-shard x{n_gpus}", "backend_options": list(args.opt),
                        "warmup_spp": warmup_spp or spp},
             "mray_segments_per_s": seg_rate, "segments_per_sample": seg_total / (samples_per_step * steps),
             "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": scene_bytes, "d2h_bytes_per_step": nfl * 4,

@@ -595,7 +595,7 @@ int check_word_result(ptb_ctx *ctx) {
     if (word != 0) {
         cudaMemset(ctx->check_word.p, 0, sizeof(int));
         return fail(ctx, PTB_ERR_STATE, "PTB_CHECK: a kernel saw an out-of-bounds index, code " + std::to_string(word) +
-                                            " (1 stack, 2 queue, 3 slot, 4 trace list, 5 ray, 6 stream, 7 node, 8 primitive)");
+                                            " (1 traversal stack, 2 queue append, 3 slot / branch mask, 5 ray index, 7 node, 8 primitive)");
     }
     return PTB_OK;
 }

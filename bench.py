@@ -196,7 +196,12 @@ EXTRAS = {
 }
 
 
+# rough wall-clock cost of an extra workload on ONE GPU in seconds (scene generation / loading + its frames), used by --time-budget
+EXTRA_COST_S = {"cornell_default": 5, "single_sphere_1080p": 3, "three_spheres_1080p": 3, "mesh_1080p": 15, "synthetic4k": 60 + 130}
+
+
 def main():
+    t_start = time.perf_counter()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -208,6 +213,9 @@ def main():
     ap.add_argument("--extras", default=None, help="'all', 'none' or a comma list of workloads measured beside the headline "
                     "(default: all for the default headline workload at full spp, none otherwise)")
     ap.add_argument("--no-cabi-multi", action="store_true", help="N > 1: skip the single-process ptb_create_multi measurement")
+    ap.add_argument("--time-budget", type=float, default=780.0,
+                    help="seconds of wall clock this run may use: an extra workload that would not fit is skipped (and listed as skipped), "
+                         "the headline line is always printed")
     ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
                     help="backend option (ptb_set_option), development only; recorded in config")
     ap.add_argument("--reduce", default="peer", choices=["peer", "nccl"],
@@ -444,6 +452,16 @@ def main():
     extra_lines = {}
     for w in extras:
         wu, wu_spp, k, ke = EXTRAS[w]
+        # every rank takes the same decision: rank 0's clock, broadcast
+        est = (60 if w == "synthetic4k" else 0) + (EXTRA_COST_S[w] - (60 if w == "synthetic4k" else 0)) / max(n_gpus, 1)
+        fits = torch.tensor([1 if (time.perf_counter() - t_start) + est <= args.time_budget else 0], dtype=torch.int32, device=dev)
+        if dist is not None:
+            dist.broadcast(fits, src=0)
+        if int(fits.item()) == 0:
+            if rank == 0:
+                extra_lines[w] = {"skipped": f"would not fit the time budget of {args.time_budget:.0f} s "
+                                             f"({time.perf_counter() - t_start:.0f} s used, ~{est:.0f} s needed)"}
+            continue
         t0 = time.perf_counter()
         try:
             r = measure(w, 0, wu, wu_spp, k, ke, "frame" if (w == "cornell_default" and not args.no_cpu_baseline) else "none")

@@ -113,7 +113,8 @@ int ptb_create(int device_id, ptb_ctx **out);
  * ptb_set_option applies to all, ptb_render / ptb_render_progressive render global sample indices
  * [spp_begin + g*spp_count/n, spp_begin + (g+1)*spp_count/n) on device g and sum the framebuffers in device order with the
  * fused peer-memory reduce+resolve kernel, ptb_get_stats reports the whole job.  The parity hooks (ptb_primary_hits, ptb_intersect)
- * run on device_ids[0].  n_devices = 1 is the same as ptb_create. */
+ * run on device_ids[0].  n_devices = 1 is the same as ptb_create.  Like every entry point that takes a context, the calls leave
+ * the calling thread's current CUDA device at the context's (first) device. */
 int ptb_create_multi(const int *device_ids, int n_devices, ptb_ctx **out);
 int ptb_device_ids(const ptb_ctx *ctx, int *ids, int cap); /* returns the number of devices the context drives */
 void ptb_destroy(ptb_ctx *ctx);

@@ -573,6 +573,8 @@ extern "C" int ptb_get_stats(const ptb_ctx *ctx, ptb_stats *out) {
         out->bvh_prims_tested += m->stats.bvh_prims_tested;
         out->render_ms = std::max(out->render_ms, m->stats.render_ms);
     }
+    // (every entry point leaves the calling thread on the context's first device, also after it has visited the members)
+    if (!ctx->members.empty()) cudaSetDevice(ctx->device);
     return PTB_OK;
 }
 

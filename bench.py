@@ -386,7 +386,12 @@ def main():
         else:
             tps = cpu["tests_per_segment"] if cpu and "tests_per_segment" in cpu else None
             if tps is None:
-                tps = {"sphere": 4.0, "gate": 7.0, "triangle": 11.0} if scene_id == "cornell" else {"sphere": 0, "gate": 0, "triangle": 0}
+                if scene_id == "cornell":    # the reference algorithm's own counts (oracle statistics): 4 spheres, 7 gates, 11.04 triangles
+                    tps = {"sphere": 4.0, "gate": 7.0, "triangle": 11.0}
+                elif st_last["n_loose_triangles"] == 0:   # sphere-only scene: intersect_scene tests every sphere for every segment
+                    tps = {"sphere": float(st_last["n_loose_objects"]), "gate": 0.0, "triangle": 0.0}
+                else:
+                    tps = {"sphere": 0.0, "gate": 0.0, "triangle": 0.0}
             tps = dict(tps, bvh_nodes=0.0)
             dominant = "k_render" if not (W * H < 2 * sms * 24 * 32) else "k_wf_shade (+ k_wf_generate, k_wf_accumulate: wavefront integrator, small frame)"
         flops_per_seg = 17.0 * (tps["sphere"] + tps["gate"]) + 45.0 * tps["triangle"] + 30.0 * tps["bvh_nodes"] + 120.0

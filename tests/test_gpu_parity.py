@@ -277,6 +277,13 @@ def test_multi_gpu_context_bit_exact():
             seen = []
             mb.render_progressive(W, H, spp, lambda img, d, t: seen.append(d), preview_interval_ms=0.0, seed=5, samples_done=done)
             assert done.value == W * H * spp
+            # a cancel flag that is already set: nothing is rendered, the frame is black, every device reports zero samples
+            cancel = C.c_int32(1)
+            img = mb.render(W, H, spp, seed=5, cancel=cancel)
+            assert mb.last_rc == A.PTB_CANCELLED and not img.any() and mb.stats()["samples"] == 0
+            # a multi-GPU context renders through ptb_render; the device-pointer entry point refuses it
+            with pytest.raises(A.BackendError):
+                mb.render_device(W, H, 1, 0)
         finally:
             mb.close()
 

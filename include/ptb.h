@@ -134,6 +134,8 @@ int ptb_flatten_loose(const ptb_scene_desc *desc, double quad_min_ratio, float *
  *   "bvh_min_spheres" scenes with at least this many spheres put them in the BVH (default 48)
  *   "integrator"      0 = auto (wavefront when the scene has a BVH or the frame is small, else megakernel), 1 = megakernel, 2 = wavefront
  *   "wavefront_paths" paths in flight per wavefront batch (default 2^25; the workspace is 0.7 KB per path)
+ *   "bvh_wide"        compressed eight-wide BVH for the wavefront trace kernel: 1 = always, 0 = never, -1 = for large sets (default)
+ *   "bvh_sah_max_prims" sets up to this size get a binned-SAH topology built on the host instead of the device LBVH (default 16384)
  *   "bvh_leaf_max" (1..8, default 2), "bvh_top_levels" (0..5: four-wide levels the trace kernel keeps in shared memory),
  *   "wf_refill", "wf_descend_min", "wf_trace_threads" (256 / 512 / 1024): traversal tuning, see DESIGN.md
  *   "quad_min_ratio"  a two-triangle mesh whose bounding-sphere radius is at least this fraction of the scene diagonal is tested

@@ -1,0 +1,223 @@
+// pt_bvh8_build.cpp -- host side of the compressed eight-wide BVH (layout and parity argument: pt_bvh8.h).
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <functional>
+#include <thread>
+
+#include "pt_bvh8.h"
+
+namespace ptb {
+
+namespace {
+
+inline double area(const Bvh8Box &b) {
+    const double dx = std::max(0.f, b.hi[0] - b.lo[0]), dy = std::max(0.f, b.hi[1] - b.lo[1]), dz = std::max(0.f, b.hi[2] - b.lo[2]);
+    return dx * dy + dy * dz + dz * dx;
+}
+
+}  // namespace
+
+int bvh8_collapse(int n, const int *left, const int *right, const int *first, const int *last, const Bvh8Box *node_box,
+                  const Bvh8Box *leaf_box, double d_bound, std::vector<uint32_t> &nodes, std::vector<int> &order) {
+    nodes.clear();
+    order.clear();
+    if (n <= 0) return 0;
+    // child ref: >= 0 binary inner node, < 0 ~leaf position
+    auto ref_first = [&](int r) { return r < 0 ? ~r : first[r]; };
+    auto ref_last = [&](int r) { return r < 0 ? ~r : last[r]; };
+    auto ref_size = [&](int r) { return ref_last(r) - ref_first(r) + 1; };
+    auto ref_box = [&](int r) -> const Bvh8Box & { return r < 0 ? leaf_box[~r] : node_box[r]; };
+    auto is_leaf = [&](int r) { return ref_size(r) <= BVH8_LEAF_MAX; };
+
+    // ---- pass 1 (sequential, breadth first): children of every wide node, their slots, the numbering of nodes and primitives
+    struct Wide {
+        int bin;          // the binary subtree this wide node stands for (-1: the single-primitive set)
+        int depth;
+        int child[8];     // per slot: child ref, or INT_MIN for an empty slot
+        uint32_t child_base, prim_base;
+    };
+    constexpr int EMPTY = INT32_MIN;
+    const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    auto parallel_for = [&](size_t begin, size_t end, const std::function<void(size_t, size_t)> &fn) {
+        const size_t cnt = end - begin;
+        if (cnt < 4096 || hw == 1) { fn(begin, end); return; }
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < hw; ++t) th.emplace_back(fn, begin + cnt * t / hw, begin + cnt * (t + 1) / hw);
+        for (auto &x : th) x.join();
+    };
+    std::vector<Wide> wide;
+    wide.reserve((size_t)n / 3 + 16);
+    wide.push_back(Wide{n == 1 ? -1 : 0, 1, {EMPTY, EMPTY, EMPTY, EMPTY, EMPTY, EMPTY, EMPTY, EMPTY}, 0u, 0u});
+    order.assign((size_t)n, 0);
+    size_t n_order = 0;
+    int max_depth = 1;
+    // level by level (a level's nodes are consecutive): children and slots in parallel, then the numbering by a prefix sum, then
+    // the next level's nodes and the primitive order in parallel (the walk is bound by cache misses on the binary nodes' boxes)
+    std::vector<uint32_t> cnt_inner, cnt_prim;
+    for (size_t lb = 0, le = 1; lb < le;) {
+        if (le >= (1u << 28)) return 0;
+        max_depth = wide[lb].depth;
+        cnt_inner.assign(le - lb + 1, 0u);
+        cnt_prim.assign(le - lb + 1, 0u);
+        parallel_for(lb, le, [&](size_t w0, size_t w1) {
+            for (size_t w = w0; w < w1; ++w) {
+                const int bin = wide[w].bin;
+                int c[8];
+                int nc = 0;
+                const Bvh8Box &nb = bin < 0 ? leaf_box[0] : node_box[bin];
+                if (bin < 0) c[nc++] = ~0;  // the whole set is one primitive
+                else if (is_leaf(bin)) c[nc++] = bin;  // (the root itself is small enough to be one leaf child)
+                else {
+                    c[nc++] = left[bin];
+                    c[nc++] = right[bin];
+                    float ar[8];
+                    ar[0] = is_leaf(c[0]) ? -1.f : (float)area(ref_box(c[0]));
+                    ar[1] = is_leaf(c[1]) ? -1.f : (float)area(ref_box(c[1]));
+                    while (nc < 8) {  // open the inner child with the largest surface area until the node is full
+                        int best = -1;
+                        float best_a = -1.f;
+                        for (int i = 0; i < nc; ++i)
+                            if (ar[i] > best_a) { best_a = ar[i]; best = i; }
+                        if (best < 0 || best_a < 0.f) break;
+                        const int b = c[best];
+                        c[best] = left[b];
+                        ar[best] = is_leaf(c[best]) ? -1.f : (float)area(ref_box(c[best]));
+                        c[nc] = right[b];
+                        ar[nc] = is_leaf(c[nc]) ? -1.f : (float)area(ref_box(c[nc]));
+                        nc++;
+                    }
+                }
+                // slots: the child towards (+x, +y, +z) bits of the node's centre; greedy on the projection of the centroid offset
+                float off[8][3];
+                for (int i = 0; i < nc; ++i) {
+                    const Bvh8Box &b = ref_box(c[i]);
+                    for (int a = 0; a < 3; ++a) off[i][a] = 0.5f * (b.lo[a] + b.hi[a]) - 0.5f * (nb.lo[a] + nb.hi[a]);
+                }
+                int slot_child[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
+                unsigned done_children = 0;
+                for (int k = 0; k < nc; ++k) {
+                    int bi = -1, bs = -1;
+                    float bv = -3e38f;
+                    for (int i = 0; i < nc; ++i) {
+                        if (done_children >> i & 1u) continue;
+                        for (int sl = 0; sl < 8; ++sl) {
+                            if (slot_child[sl] >= 0) continue;
+                            const float v = (sl & 1 ? off[i][0] : -off[i][0]) + (sl & 2 ? off[i][1] : -off[i][1]) + (sl & 4 ? off[i][2] : -off[i][2]);
+                            if (v > bv) { bv = v; bi = i; bs = sl; }
+                        }
+                    }
+                    slot_child[bs] = bi;
+                    done_children |= 1u << bi;
+                }
+                uint32_t ni = 0, np = 0;
+                for (int sl = 0; sl < 8; ++sl) {
+                    const int r = slot_child[sl] < 0 ? EMPTY : c[slot_child[sl]];
+                    wide[w].child[sl] = r;
+                    if (r == EMPTY) continue;
+                    if (is_leaf(r)) np += (uint32_t)ref_size(r); else ni++;
+                }
+                cnt_inner[w - lb] = ni;
+                cnt_prim[w - lb] = np;
+            }
+        });
+        // numbering: inner children consecutive in slot order, primitives of leaf children consecutive in slot order
+        size_t next_node = le, next_prim = n_order;
+        for (size_t w = lb; w < le; ++w) {
+            wide[w].child_base = (uint32_t)next_node;
+            wide[w].prim_base = (uint32_t)next_prim;
+            next_node += cnt_inner[w - lb];
+            next_prim += cnt_prim[w - lb];
+        }
+        if (next_prim > (size_t)n) return 0;
+        wide.resize(next_node, Wide{0, 0, {EMPTY, EMPTY, EMPTY, EMPTY, EMPTY, EMPTY, EMPTY, EMPTY}, 0u, 0u});
+        parallel_for(lb, le, [&](size_t w0, size_t w1) {
+            for (size_t w = w0; w < w1; ++w) {
+                size_t at_node = wide[w].child_base, at_prim = wide[w].prim_base;
+                for (int sl = 0; sl < 8; ++sl) {
+                    const int r = wide[w].child[sl];
+                    if (r == EMPTY) continue;
+                    if (is_leaf(r)) {
+                        for (int k = ref_first(r); k <= ref_last(r); ++k) order[at_prim++] = k;
+                    } else {
+                        wide[at_node].bin = r;
+                        wide[at_node].depth = wide[w].depth + 1;
+                        at_node++;
+                    }
+                }
+            }
+        });
+        n_order = next_prim;
+        lb = le;
+        le = next_node;
+    }
+    order.resize(n_order);
+
+    // ---- pass 2 (parallel): grid of every node, quantised child boxes, meta bytes
+    // the smallest grid step that keeps the traversal's decode error below one step (pt_bvh8.h): 8 u D
+    const double min_step = 8.0 * 5.9604645e-8 * std::max(d_bound, 1e-30);
+    const int min_e = (int)std::ceil(std::log2(min_step));
+    nodes.assign(24 * wide.size(), 0u);
+    auto pack = [&](size_t w0, size_t w1) {
+        for (size_t w = w0; w < w1; ++w) {
+            const Wide &W = wide[w];
+            const Bvh8Box &nb = W.bin < 0 ? leaf_box[0] : node_box[W.bin];
+            float p[3];
+            int e[3];
+            double inv_step[3];
+            for (int a = 0; a < 3; ++a) {
+                // origin one step below the node's lower corner, steps 2^e with (extent + 2 steps) <= 252 steps and step >= min_step
+                const double ext = std::max(0.0, (double)nb.hi[a] - (double)nb.lo[a]);
+                int ex = min_e;
+                if (ext > 0.0) {
+                    int fe;
+                    std::frexp(ext / 250.0, &fe);  // ext / 250 = m * 2^fe, 0.5 <= m < 1: 2^fe >= ext / 250
+                    ex = std::max(min_e, fe);
+                }
+                ex = std::max(-100, std::min(100, ex));
+                e[a] = ex;
+                const double step = std::ldexp(1.0, ex);
+                inv_step[a] = std::ldexp(1.0, -ex);
+                const double pd = (double)nb.lo[a] - step;
+                float pf = (float)pd;
+                if ((double)pf > pd) pf = std::nextafterf(pf, -INFINITY);  // rounded DOWN
+                p[a] = pf;
+            }
+            uint32_t imask = 0;
+            uint8_t meta[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[6][8];
+            std::memset(q, 0, sizeof q);
+            int prim_off = 0;
+            for (int sl = 0; sl < 8; ++sl) {
+                const int r = W.child[sl];
+                if (r == EMPTY) continue;
+                const Bvh8Box &b = ref_box(r);
+                for (int a = 0; a < 3; ++a) {
+                    const double lo = std::floor(((double)b.lo[a] - (double)p[a]) * inv_step[a]) - 1.0;
+                    const double hi = std::ceil(((double)b.hi[a] - (double)p[a]) * inv_step[a]) + 1.0;
+                    q[a][sl] = (uint8_t)std::max(0.0, std::min(255.0, lo));
+                    q[3 + a][sl] = (uint8_t)std::max(0.0, std::min(255.0, hi));
+                }
+                if (is_leaf(r)) {
+                    const int cnt = ref_size(r);
+                    meta[sl] = (uint8_t)((((1u << cnt) - 1u) << 5) | (uint32_t)prim_off);
+                    prim_off += cnt;
+                } else {
+                    imask |= 1u << sl;
+                    meta[sl] = (uint8_t)(0x20u | (24u + (uint32_t)sl));
+                }
+            }
+            uint32_t *rec = &nodes[24 * w];
+            std::memcpy(&rec[0], &p[0], 4); std::memcpy(&rec[1], &p[1], 4); std::memcpy(&rec[2], &p[2], 4);
+            rec[3] = (uint32_t)(e[0] + 127) | (uint32_t)(e[1] + 127) << 8 | (uint32_t)(e[2] + 127) << 16 | imask << 24;
+            rec[4] = W.child_base; rec[5] = W.prim_base;
+            std::memcpy(&rec[6], &meta[0], 4); std::memcpy(&rec[7], &meta[4], 4);
+            for (int k = 0; k < 6; ++k) { std::memcpy(&rec[8 + 2 * k], &q[k][0], 4); std::memcpy(&rec[9 + 2 * k], &q[k][4], 4); }
+        }
+    };
+    parallel_for(0, wide.size(), pack);
+    return max_depth;
+}
+
+}  // namespace ptb

@@ -12,6 +12,7 @@
 #include <cstring>
 
 #include "pt_bvh.cuh"
+#include "pt_bvh8.h"
 #include "pt_bvh_build.h"
 #include "pt_launch.h"
 
@@ -368,6 +369,18 @@ void sah_hierarchy(const std::vector<HostBox> &box, SahOut &o) {
     o.parent_inner[0] = -1;
 }
 
+// padded primitive boxes in leaf order (for the host-side wide collapse); wide-order index map = sorted index of the leaf position
+__global__ void k_leaf_boxes(const int *__restrict__ idx, const float4 *__restrict__ blo, const float4 *__restrict__ bhi, int n,
+                             float4 *__restrict__ lo, float4 *__restrict__ hi) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    lo[i] = blo[idx[i]]; hi[i] = bhi[idx[i]];
+}
+__global__ void k_compose_order(const int *__restrict__ idx, const int *__restrict__ order, int n, int *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = idx[order[i]];
+}
+
 template <typename T>
 cudaError_t dev_alloc(T **p, size_t n) { return cudaMalloc(reinterpret_cast<void **>(p), std::max<size_t>(n, 1) * sizeof(T)); }
 
@@ -412,6 +425,8 @@ void bvh_release(BvhDevice &b) {
     if (b.nodes) cudaFree(b.nodes);
     if (b.tris) cudaFree(b.tris);
     if (b.top) cudaFree(b.top);
+    if (b.nodes8) cudaFree(b.nodes8);
+    if (b.tris8) cudaFree(b.tris8);
     if (b.top_count) cudaFree(b.top_count);
     b = BvhDevice{};
 }
@@ -429,6 +444,8 @@ cudaError_t bvh_build(const ptb_scene_desc &desc, const std::vector<char> &in_bv
     ds.bvh_root = BVH_EMPTY_REF;
     ds.bvh_nodes = nullptr; ds.bvh_tri = nullptr; ds.bvh_e2 = nullptr; ds.bvh_fin = nullptr; ds.n_bvh_nodes = 0;
     ds.bvh_top = nullptr; ds.n_bvh_top = 0; ds.n_bvh_prims = 0;
+    ds.bvh8_nodes = nullptr; ds.n_bvh8_nodes = 0; ds.bvh8_tri = nullptr; ds.bvh8_e2 = nullptr; ds.bvh8_fin = nullptr;
+    out.n_nodes8 = 0;
     ds.bvh_lo = mk3(0.f, 0.f, 0.f); ds.bvh_hi = mk3(0.f, 0.f, 0.f);
     if (build_ms) *build_ms = 0.0;
 
@@ -634,6 +651,62 @@ cudaError_t bvh_build(const ptb_scene_desc &desc, const std::vector<char> &in_bv
     }
     k_gather_prims<<<B, T, 0, st>>>(d_recs, d_idx2, n, out.tris, out.tris + 2 * (size_t)n, out.tris + 3 * (size_t)n);
     BV(cudaGetLastError());
+    if ((opt.wide == 1 || (opt.wide < 0 && n > opt.sah_max_prims)) && n > 1) {
+        // ---- compressed eight-wide BVH over the same binary hierarchy: collapse on the host (pt_bvh8_build.cpp), upload
+        float4 *d_llo = nullptr, *d_lhi = nullptr;
+        int *d_order = nullptr;
+        std::vector<int> h_left((size_t)n_inner), h_right((size_t)n_inner), h_first((size_t)n_inner), h_last((size_t)n_inner);
+        std::vector<float4> h_nlo((size_t)n_inner), h_nhi((size_t)n_inner), h_llo((size_t)n), h_lhi((size_t)n);
+        cudaError_t we = cudaSuccess;
+        auto W = [&](cudaError_t e) { if (we == cudaSuccess) we = e; return e == cudaSuccess; };
+        W(dev_alloc(&d_llo, (size_t)n)); W(dev_alloc(&d_lhi, (size_t)n)); W(dev_alloc(&d_order, (size_t)n));
+        if (we == cudaSuccess) {
+            k_leaf_boxes<<<B, T, 0, st>>>(d_idx2, d_blo, d_bhi, n, d_llo, d_lhi);
+            const size_t bi = sizeof(int) * (size_t)n_inner, bf = sizeof(float4) * (size_t)n_inner;
+            W(cudaMemcpyAsync(h_left.data(), d_left, bi, cudaMemcpyDeviceToHost, st));
+            W(cudaMemcpyAsync(h_right.data(), d_right, bi, cudaMemcpyDeviceToHost, st));
+            W(cudaMemcpyAsync(h_first.data(), d_first, bi, cudaMemcpyDeviceToHost, st));
+            W(cudaMemcpyAsync(h_last.data(), d_last, bi, cudaMemcpyDeviceToHost, st));
+            W(cudaMemcpyAsync(h_nlo.data(), d_nlo, bf, cudaMemcpyDeviceToHost, st));
+            W(cudaMemcpyAsync(h_nhi.data(), d_nhi, bf, cudaMemcpyDeviceToHost, st));
+            W(cudaMemcpyAsync(h_llo.data(), d_llo, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost, st));
+            W(cudaMemcpyAsync(h_lhi.data(), d_lhi, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost, st));
+            W(cudaStreamSynchronize(st));
+        }
+        if (we == cudaSuccess) {
+            std::vector<Bvh8Box> nb((size_t)n_inner), lb((size_t)n);
+            for (int i = 0; i < n_inner; ++i) nb[i] = Bvh8Box{{h_nlo[i].x, h_nlo[i].y, h_nlo[i].z}, {h_nhi[i].x, h_nhi[i].y, h_nhi[i].z}};
+            for (int i = 0; i < n; ++i) lb[i] = Bvh8Box{{h_llo[i].x, h_llo[i].y, h_llo[i].z}, {h_lhi[i].x, h_lhi[i].y, h_lhi[i].z}};
+            std::vector<uint32_t> wn;
+            std::vector<int> order;
+            const int wdepth = bvh8_collapse(n, h_left.data(), h_right.data(), h_first.data(), h_last.data(), nb.data(), lb.data(),
+                                             (double)D + coord_max, wn, order);
+            if (wdepth > 0 && wdepth + 2 <= BVH_STACK && (int)order.size() == n) {
+                const size_t nw = wn.size() / 24;
+                if (out.cap_nodes8 < nw) {
+                    if (out.nodes8) cudaFree(out.nodes8);
+                    out.nodes8 = nullptr; out.cap_nodes8 = 0;
+                    if (W(dev_alloc(&out.nodes8, 6 * nw))) out.cap_nodes8 = nw;
+                }
+                if (out.cap_tris8 < (size_t)n) {
+                    if (out.tris8) cudaFree(out.tris8);
+                    out.tris8 = nullptr; out.cap_tris8 = 0;
+                    if (W(dev_alloc(&out.tris8, 4 * (size_t)n))) out.cap_tris8 = (size_t)n;
+                }
+                if (we == cudaSuccess) {
+                    W(cudaMemcpyAsync(out.nodes8, wn.data(), wn.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+                    W(cudaMemcpyAsync(d_order, order.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, st));
+                    k_compose_order<<<B, T, 0, st>>>(d_idx2, d_order, n, d_idx);  // (d_idx is free again: the sort has consumed it)
+                    k_gather_prims<<<B, T, 0, st>>>(d_recs, d_idx, n, out.tris8, out.tris8 + 2 * (size_t)n, out.tris8 + 3 * (size_t)n);
+                    W(cudaGetLastError());
+                    W(cudaStreamSynchronize(st));  // (the host vectors go out of scope)
+                    if (we == cudaSuccess) out.n_nodes8 = (unsigned)nw;
+                }
+            }
+        }
+        cudaFree(d_llo); cudaFree(d_lhi); cudaFree(d_order);
+        if (we != cudaSuccess) { err = "wide BVH build"; rc = we; goto done; }
+    }
     BV(cudaEventRecord(ev1, st));
     BV(cudaStreamSynchronize(st));
     {
@@ -645,6 +718,10 @@ cudaError_t bvh_build(const ptb_scene_desc &desc, const std::vector<char> &in_bv
     ds.bvh_nodes = out.nodes; ds.bvh_tri = out.tris; ds.bvh_e2 = out.tris + 2 * (size_t)n; ds.bvh_fin = out.tris + 3 * (size_t)n;
     ds.n_bvh_nodes = n_alive; ds.n_bvh_prims = n;
     ds.bvh_top = out.top; ds.n_bvh_top = n_top;
+    if (out.n_nodes8 > 0) {
+        ds.bvh8_nodes = out.nodes8; ds.n_bvh8_nodes = (int)out.n_nodes8; ds.bvh8_magic = 0x4B000000u;
+        ds.bvh8_tri = out.tris8; ds.bvh8_e2 = out.tris8 + 2 * (size_t)n; ds.bvh8_fin = out.tris8 + 3 * (size_t)n;
+    }
     ds.bvh_lo = mk3(h_root[0].x, h_root[0].y, h_root[0].z); ds.bvh_hi = mk3(h_root[1].x, h_root[1].y, h_root[1].z);
 
 done:

@@ -70,12 +70,13 @@ __device__ __forceinline__ void closest_hit_loose(const float4 *__restrict__ s_o
 __device__ __forceinline__ void finish_hit(const DScene &sc, const float4 *__restrict__ s_obj, const float4 *__restrict__ s_tri,
                                            const Hit &h, V3 o, V3 d, int &obj, int &tri, V3 &x, V3 &n) {
     x = o + d * h.t;  // mod.rs:430 / :604
-    const int k = h.ref & (REF_SPHERE_BIT - 1);
+    const int k = h.ref & REF_INDEX_MASK;
     if (h.ref & REF_BVH_BIT) {
-        const float4 F = __ldg(&sc.bvh_fin[k]);
+        const bool wide = (h.ref & REF_WIDE_BIT) != 0;
+        const float4 F = __ldg(wide ? &sc.bvh8_fin[k] : &sc.bvh_fin[k]);
         obj = __float_as_int(F.w);
         if (h.ref & REF_SPHERE_BIT) { tri = -1; n = normalize(x - xyz(F)); }
-        else { tri = __float_as_int(__ldg(&sc.bvh_tri[2 * k + 1]).w); n = xyz(F); }
+        else { tri = __float_as_int(__ldg(wide ? &sc.bvh8_tri[2 * k + 1] : &sc.bvh_tri[2 * k + 1]).w); n = xyz(F); }
     } else if (h.ref & REF_SPHERE_BIT) {
         const float4 sph = s_obj[k], mb = s_obj[k + 1];
         obj = __float_as_int(mb.w);

@@ -23,6 +23,8 @@
 // branches 1..3 exist is recorded per path by the split that creates them (branch_mask), so slots are neither cleared nor
 // read for branches that never existed.
 // Queue entries are 4 x float4 (o|path, d|depth+code, T, L) in SoA arrays: coalesced 16-byte loads and stores.
+#include "pt_bvh8.cuh"
+#include "pt_bvh8.h"
 #include "pt_launch.h"
 #include "pt_scene_dev.cuh"
 #include "pt_wavefront.h"
@@ -223,6 +225,158 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_wf_trace(const DSce
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// The same job through the compressed eight-wide BVH (pt_bvh8.h): one node fetch tests eight quantised child boxes, the children
+// are visited in the fixed order of the ray's direction octant (nothing is sorted) and ONE stack entry -- (child base, hit mask)
+// -- stands for all postponed children of a node.  Primitives of leaf children that are hit are tested right after the node.
+// Shared memory: [the first nodes in breadth-first order (<= BVH8_TOP_MAX, 112-byte pitch)] [traversal stacks]
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int TOP8_PITCH = 7;  // uint4 per shared-memory node: 80 bytes of node + padding that spreads diverged lanes over the banks
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_wf_trace8(const DScene sc, const WfQueue q, const int *__restrict__ ctr,
+                                                                      int *__restrict__ fetch_ptr, unsigned long long *__restrict__ counters,
+                                                                      const int wf_refill, const int wf_descend_min) {
+    extern __shared__ float4 smem[];
+    uint4 *const s_top = reinterpret_cast<uint4 *>(smem);
+    const int n_top = min(sc.n_bvh8_nodes, BVH8_TOP_MAX);
+    int2 *const s_stack = reinterpret_cast<int2 *>(s_top + TOP8_PITCH * n_top);
+    for (int i = threadIdx.x; i < 5 * n_top; i += THREADS) s_top[(i / 5) * TOP8_PITCH + (i % 5)] = __ldg(&sc.bvh8_nodes[(i / 5) * BVH8_NODE_F4 + (i % 5)]);
+    __syncthreads();
+    const int n = ctr[0];  // the front part of the queue: the segments that can reach BVH geometry
+    const int chunk = max(32, min(WF_CHUNK, (n / (int)(gridDim.x * (THREADS / 32) * 4)) & ~31));
+    unsigned n_nodes = 0, n_prims = 0;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    bool busy = false, exhausted = false;
+    int w_next = 0, w_end = 0;  // warp-uniform
+    int ray_idx = 0;
+    V3 o = mk3(0.f, 0.f, 0.f), d = mk3(0.f, 0.f, 1.f), id = mk3(1.f, 1.f, 1.f);
+    Hit best;
+    best.t = 0.f; best.prio = PRIO_NONE; best.ref = REF_NONE;
+    int sp = 0, gate_obj = -1;
+    bool gate_pass = false;
+    unsigned ng_base = 0, ng_mask = 0, tg_base = 0, tg_mask = 0, octinv = 0;  // current node group / primitive group
+    int2 l_stack[BVH_STACK - WF_SSTACK];
+#define PTB_STK_LD(i) ((i) < WF_SSTACK ? s_stack[(i) * THREADS + threadIdx.x] : l_stack[(i) - WF_SSTACK])
+#define PTB_STK_ST(i, v)                                                        \
+    do {                                                                        \
+        if ((i) < WF_SSTACK) s_stack[(i) * THREADS + threadIdx.x] = (v);        \
+        else if (PTB_CHECKED((i) < BVH_STACK, PTB_CHK_STACK, sc.check)) l_stack[(i) - WF_SSTACK] = (v); \
+    } while (0)
+
+    for (;;) {
+        const unsigned busy_mask = __ballot_sync(0xffffffffu, busy);
+        const int n_idle = 32 - __popc(busy_mask);
+        if (!exhausted && (n_idle >= wf_refill || busy_mask == 0u)) {
+            if (w_next >= w_end) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(fetch_ptr, chunk);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                w_next = base;
+                w_end = min(base + chunk, n);
+                if (base >= n) exhausted = true;
+            }
+            const int idx = w_next + __popc(~busy_mask & lt_mask);
+            const bool got = !busy && idx < w_end;
+            w_next = min(w_next + n_idle, w_end);
+            if (got) {
+                const int r = idx;
+                if (PTB_CHECKED(r >= 0 && r < q.cap, PTB_CHK_RAY, sc.check)) {
+                    const float4 qo = __ldcs(&q.o[r]), qd = __ldcs(&q.d[r]);  // streaming: keep the L2 for the BVH
+                    o = mk3(qo.x, qo.y, qo.z); d = mk3(qd.x, qd.y, qd.z);
+                    ray_idx = r;
+                    best.t = __ldcs(&q.hit_t[r]); best.ref = __ldcs(&q.hit_ref[r]); best.prio = __ldcs(&q.hit_prio[r]);
+                    id = mk3(safe_rcp_dir(d.x), safe_rcp_dir(d.y), safe_rcp_dir(d.z));
+                    octinv = bvh8_octinv(id.x, id.y, id.z);
+                    ng_base = 0u; ng_mask = 0x80000000u;  // "the root is a hit inner child of a group that starts at node 0"
+                    tg_mask = 0u; sp = 0; gate_obj = -1;
+                    busy = true;
+                }
+            }
+        }
+        if (__ballot_sync(0xffffffffu, busy) == 0u) break;
+        if (busy) {
+            for (;;) {  // node phase: visit postponed children until primitives turn up or the ray is done
+                if (ng_mask <= 0x00ffffffu) {  // the current group has no inner child left: take the next group
+                    if (sp == 0) break;
+                    --sp;
+                    const int2 e_ = PTB_STK_LD(sp);
+                    ng_base = (unsigned)e_.x; ng_mask = (unsigned)e_.y;
+                }
+                const int bit = 31 - __clz((int)ng_mask);  // first in the octant's visiting order
+                ng_mask &= ~(1u << bit);
+                const unsigned slot = (unsigned)(bit - 24) ^ octinv;
+                const unsigned node = ng_base + (unsigned)__popc(ng_mask & 0xffu & ((1u << slot) - 1u));
+                if (ng_mask > 0x00ffffffu) { PTB_STK_ST(sp, make_int2((int)ng_base, (int)ng_mask)); sp++; }
+                // five 16-byte words from the shared-memory copy or from global memory, into the same registers either way
+                const bool in_top = (int)node < n_top;
+                (void)PTB_CHECKED((int)node < sc.n_bvh8_nodes, PTB_CHK_NODE, sc.check);
+                const uint4 *ps_ = s_top + TOP8_PITCH * (in_top ? node : 0u);
+                const uint4 *pg_ = sc.bvh8_nodes + (size_t)BVH8_NODE_F4 * (in_top ? 0u : node);
+                const uint4 a0 = in_top ? ps_[0] : __ldg(pg_), a1 = in_top ? ps_[1] : __ldg(pg_ + 1), a2 = in_top ? ps_[2] : __ldg(pg_ + 2),
+                            a3 = in_top ? ps_[3] : __ldg(pg_ + 3), a4 = in_top ? ps_[4] : __ldg(pg_ + 4);
+                Bvh8Node nd;
+                nd.w[0] = a0.x; nd.w[1] = a0.y; nd.w[2] = a0.z; nd.w[3] = a0.w; nd.w[4] = a1.x; nd.w[5] = a1.y; nd.w[6] = a1.z; nd.w[7] = a1.w;
+                nd.w[8] = a2.x; nd.w[9] = a2.y; nd.w[10] = a2.z; nd.w[11] = a2.w; nd.w[12] = a3.x; nd.w[13] = a3.y; nd.w[14] = a3.z; nd.w[15] = a3.w;
+                nd.w[16] = a4.x; nd.w[17] = a4.y; nd.w[18] = a4.z; nd.w[19] = a4.w;
+                n_nodes++;
+                const unsigned hits = bvh8_node_hits(nd, o.x, o.y, o.z, id.x, id.y, id.z, best.t, octinv, sc.bvh8_magic);
+                ng_base = nd.w[4]; ng_mask = (hits & 0xff000000u) | (nd.w[3] >> 24);
+                tg_base = nd.w[5]; tg_mask = hits & 0x00ffffffu;
+                if (tg_mask) break;
+                if (__popc(__activemask()) < wf_descend_min) break;  // let the lanes that hold primitives get on with it
+            }
+            while (tg_mask) {  // primitives of the leaf children that were hit (reference arithmetic, prio tie-break, lazy gate)
+                const int b_ = 31 - __clz((int)tg_mask);
+                tg_mask &= ~(1u << b_);
+                const int k = (int)tg_base + b_;
+                n_prims++;
+                if (!PTB_CHECKED(k < sc.n_bvh_prims, PTB_CHK_PRIM, sc.check)) continue;
+                const F8 ae_ = ld256(sc.bvh8_tri + 2 * (size_t)k);
+                const float4 A = ae_.a, E1 = ae_.b, E2 = __ldg(&sc.bvh8_e2[k]);
+                const bool is_sphere = __float_as_int(E1.w) < 0;
+                float tt;
+                if (is_sphere) tt = sphere_t(xyz(A), E1.x, o, d);
+                else tt = triangle_t(xyz(A), xyz(E1), xyz(E2), o, d);
+                const uint32_t prio = (uint32_t)__float_as_int(E2.w);
+                if (tt > 0.0f && (tt < best.t || (tt == best.t && prio < best.prio))) {
+                    bool ok = true;
+                    if (!is_sphere) {  // mesh gate (mod.rs:267-277), evaluated lazily and cached per object
+                        const int obj = __float_as_int(A.w);
+                        if (obj != gate_obj) {
+                            const float4 g = __ldg(&sc.obj_gate[obj]);
+                            gate_pass = sphere_gate(xyz(g), g.w, o, d);
+                            gate_obj = obj;
+                        }
+                        ok = gate_pass;
+                    }
+                    if (ok) {
+                        best.t = tt; best.prio = prio;
+                        best.ref = REF_BVH_BIT | REF_WIDE_BIT | (is_sphere ? REF_SPHERE_BIT : 0) | k;
+                    }
+                }
+            }
+            if (ng_mask <= 0x00ffffffu && sp == 0) {  // nothing left to visit
+                __stcs(&q.hit_t[ray_idx], best.t);
+                __stcs(&q.hit_ref[ray_idx], best.ref);
+                busy = false;
+            }
+        }
+    }
+#undef PTB_STK_LD
+#undef PTB_STK_ST
+    for (int off = 16; off > 0; off >>= 1) {
+        n_nodes += __shfl_down_sync(0xffffffffu, n_nodes, off);
+        n_prims += __shfl_down_sync(0xffffffffu, n_prims, off);
+    }
+    if (lane == 0 && (n_nodes | n_prims)) {
+        atomicAdd(&counters[1], (unsigned long long)n_nodes);
+        atomicAdd(&counters[2], (unsigned long long)n_prims);
+    }
+}
+
 // material arm of every queued segment; appends the next bounce
 // (four CTAs per SM: 64 registers with ~100 bytes of spills beat 92 registers at two CTAs -- mesh.json 1080p 996 -> 1164 Mpaths/s, the
 //  kernel waits on its queue loads and needs the warps; three CTAs: 1124)
@@ -384,9 +538,11 @@ struct TraceLaunch {
 
 template <int THREADS>
 cudaError_t trace_config(const DScene &sc, int sm_count, TraceLaunch &t) {
-    t.kern = k_wf_trace<THREADS>;
+    const bool wide = sc.n_bvh8_nodes > 0;
+    t.kern = wide ? k_wf_trace8<THREADS> : k_wf_trace<THREADS>;
     t.threads = THREADS;
-    t.smem = sizeof(float4) * TOP_PITCH * (size_t)sc.n_bvh_top + sizeof(int2) * WF_SSTACK * THREADS;
+    t.smem = (wide ? sizeof(uint4) * TOP8_PITCH * (size_t)std::min(sc.n_bvh8_nodes, BVH8_TOP_MAX) : sizeof(float4) * TOP_PITCH * (size_t)sc.n_bvh_top) +
+             sizeof(int2) * WF_SSTACK * THREADS;
     cudaError_t e = cudaFuncSetAttribute(t.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
@@ -437,7 +593,8 @@ cudaError_t wavefront_render(const DScene &sc, const RenderArgs &a, WfWorkspace 
             const WfQueue &cur = w.q[b & 1], &nxt = w.q[(b + 1) & 1];
             int *ctr = w.counters + WF_CTR_STRIDE * b;
             if (has_bvh) {
-                tl.kern<<<tl.blocks, tl.threads, tl.smem, st>>>(sc, cur, ctr, ctr + 2, a.segment_counter, opt.refill, opt.descend_min);
+                tl.kern<<<tl.blocks, tl.threads, tl.smem, st>>>(sc, cur, ctr, ctr + 2, a.segment_counter, opt.refill,
+                                                                sc.n_bvh8_nodes > 0 ? opt.descend_min_wide : opt.descend_min);
                 (*launches)++;
             }
             k_wf_shade<<<wide, 256, smem, st>>>(sc, cur, ctr, nxt, ctr + WF_CTR_STRIDE, w.slots, w.branch_mask, (unsigned)n_paths, npix, s0,

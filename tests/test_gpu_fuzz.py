@@ -94,6 +94,9 @@ def test_random_scene_matches_oracle(tmp_path, idx, n_spheres, n_inline, n_file_
                  {"integrator": 1, "bvh_min_tris": 1e18, "bvh_min_spheres": 1e18}, {"integrator": 2, "bvh_min_tris": 2, "bvh_min_spheres": 2},
                  {"integrator": 2, "bvh_leaf_max": 4, "bvh_min_tris": 2, "bvh_min_spheres": 2},
                  {"integrator": 2, "bvh_sah_max_prims": 0, "bvh_min_tris": 2, "bvh_min_spheres": 2},   # device LBVH instead of the host SAH topology
+                 {"integrator": 2, "bvh_wide": 1, "bvh_min_tris": 2, "bvh_min_spheres": 2},            # compressed eight-wide BVH in the trace kernel
+                 {"integrator": 2, "bvh_wide": 1, "bvh_sah_max_prims": 0, "wavefront_paths": 6000, "wf_trace_threads": 256, "bvh_min_tris": 2,
+                  "bvh_min_spheres": 2},
                  {"integrator": 1, "bvh_sah_max_prims": 0, "bvh_leaf_max": 3, "bvh_min_tris": 2, "bvh_min_spheres": 2},
                  {"integrator": 2, "wf_refill": 1, "wf_descend_min": 30, "bvh_top_levels": 2, "bvh_min_tris": 2, "bvh_min_spheres": 2,
                   "wavefront_paths": 7000},

@@ -194,8 +194,13 @@ int bvh8_collapse(int n, const int *left, const int *right, const int *first, co
                 if (r == EMPTY) continue;
                 const Bvh8Box &b = ref_box(r);
                 for (int a = 0; a < 3; ++a) {
-                    const double lo = std::floor(((double)b.lo[a] - (double)p[a]) * inv_step[a]) - 1.0;
-                    const double hi = std::ceil(((double)b.hi[a] - (double)p[a]) * inv_step[a]) + 1.0;
+#ifdef PTB_BVH8_NO_MARGIN  // negative control of tests/test_bvh8_cpu.py only: without the extra step the traversal must lose hits
+                    const double margin = 0.0;
+#else
+                    const double margin = 1.0;  // one step for the traversal's decode error (pt_bvh8.h)
+#endif
+                    const double lo = std::floor(((double)b.lo[a] - (double)p[a]) * inv_step[a]) - margin;
+                    const double hi = std::ceil(((double)b.hi[a] - (double)p[a]) * inv_step[a]) + margin;
                     q[a][sl] = (uint8_t)std::max(0.0, std::min(255.0, lo));
                     q[3 + a][sl] = (uint8_t)std::max(0.0, std::min(255.0, hi));
                 }

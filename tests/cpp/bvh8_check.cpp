@@ -79,6 +79,17 @@ int main(int argc, char **argv) {
         for (int k = 0; k < 3; ++k) { o[k] = -60.f + 120.f * U(rng); d[k] = -1.f + 2.f * U(rng); }
         if (r % 7 == 0) d[(r / 7) % 3] = 0.f;                       // axis-parallel components
         if (r % 11 == 0) { o[0] = 0.f; o[1] = -12.f; o[2] = 0.f; }  // from inside the dense ball
+        if (r % 5 == 0) {  // grazing: aimed at a corner / edge point of some box, from near or far
+            const Bvh8Box &b = leaf[(size_t)(U(rng) * n) % n];
+            float tgt[3];
+            for (int k = 0; k < 3; ++k) {
+                const float u = U(rng);
+                tgt[k] = u < 0.4f ? b.lo[k] : (u < 0.8f ? b.hi[k] : b.lo[k] + (b.hi[k] - b.lo[k]) * U(rng));
+                tgt[k] += (U(rng) - 0.5f) * 2e-6f * (1.0f + std::fabs(tgt[k]));
+            }
+            if (r % 10 == 0) for (int k = 0; k < 3; ++k) o[k] = tgt[k] + (U(rng) - 0.5f) * 0.02f;   // origin almost on the box
+            for (int k = 0; k < 3; ++k) d[k] = tgt[k] - o[k];
+        }
         const float len = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
         if (len == 0.f) continue;
         for (int k = 0; k < 3; ++k) d[k] /= len;

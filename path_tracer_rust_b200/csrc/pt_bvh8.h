@@ -29,7 +29,7 @@ namespace ptb {
 
 constexpr int BVH8_NODE_F4 = 6;       // float4 per node
 constexpr int BVH8_LEAF_MAX = 1;      // primitives per leaf child (measured: 1 -> 234, 2 -> 224, 3 -> 215 Mpaths/s on the synthetic scene)
-constexpr int BVH8_TOP_MAX = 512;     // nodes (breadth first from the root) the trace kernel keeps in shared memory
+constexpr int BVH8_TOP_MAX = 1024;    // nodes (breadth first from the root) the trace kernel keeps in shared memory
 
 struct Bvh8Box { float lo[3], hi[3]; };
 

@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_wf_trace8(const DSc
                                                                       const int wf_refill, const int wf_descend_min) {
     extern __shared__ float4 smem[];
     uint4 *const s_top = reinterpret_cast<uint4 *>(smem);
-    const int n_top = min(sc.n_bvh8_nodes, BVH8_TOP_MAX);
+    const int n_top = sc.n_bvh8_top;
     int2 *const s_stack = reinterpret_cast<int2 *>(s_top + TOP8_PITCH * n_top);
     for (int i = threadIdx.x; i < 5 * n_top; i += THREADS) s_top[(i / 5) * TOP8_PITCH + (i % 5)] = __ldg(&sc.bvh8_nodes[(i / 5) * BVH8_NODE_F4 + (i % 5)]);
     __syncthreads();
@@ -541,7 +541,7 @@ cudaError_t trace_config(const DScene &sc, int sm_count, TraceLaunch &t) {
     const bool wide = sc.n_bvh8_nodes > 0;
     t.kern = wide ? k_wf_trace8<THREADS> : k_wf_trace<THREADS>;
     t.threads = THREADS;
-    t.smem = (wide ? sizeof(uint4) * TOP8_PITCH * (size_t)std::min(sc.n_bvh8_nodes, BVH8_TOP_MAX) : sizeof(float4) * TOP_PITCH * (size_t)sc.n_bvh_top) +
+    t.smem = (wide ? sizeof(uint4) * TOP8_PITCH * (size_t)sc.n_bvh8_top : sizeof(float4) * TOP_PITCH * (size_t)sc.n_bvh_top) +
              sizeof(int2) * WF_SSTACK * THREADS;
     cudaError_t e = cudaFuncSetAttribute(t.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem);
     if (e != cudaSuccess) return e;
@@ -555,8 +555,10 @@ cudaError_t trace_config(const DScene &sc, int sm_count, TraceLaunch &t) {
 }  // namespace
 
 // renders samples [a.spp_begin, a.spp_begin + a.spp_count) of every pixel into a.sum_rgb; adds the kernels launched to *launches
-cudaError_t wavefront_render(const DScene &sc, const RenderArgs &a, WfWorkspace &w, int sm_count, const WfOptions &opt, cudaStream_t st,
+cudaError_t wavefront_render(const DScene &scene, const RenderArgs &a, WfWorkspace &w, int sm_count, const WfOptions &opt, cudaStream_t st,
                              unsigned *launches) {
+    DScene sc = scene;
+    sc.n_bvh8_top = std::max(0, std::min(std::min(sc.n_bvh8_nodes, BVH8_TOP_MAX), opt.top8_nodes));
     const unsigned npix = (unsigned)a.width * (unsigned)a.height;
     unsigned K = (unsigned)std::max<size_t>(1, opt.target_paths / npix);
     if ((unsigned long long)K > a.spp_count) K = (unsigned)a.spp_count;

@@ -38,6 +38,9 @@ struct WfWorkspace {
 struct WfOptions {
     size_t target_paths = 1u << 25;  // paths in flight per batch (measured on B200: 2^23 -> 2^25 = +15 % synthetic, +8 % mesh.json; 2^26 +3 % more)
     int refill = 8;                  // idle lanes of a warp that trigger a refill from the queue
+    int top8_nodes = 0;              // nodes of the eight-wide BVH (breadth first) staged in shared memory, <= BVH8_TOP_MAX.  Measured on
+                                     // B200: 0 / 73 / 256 / 512 nodes = 236.9 / 235.5 / 235.6 / 237.3 Mpaths/s -- the 96-byte nodes of the top
+                                     // levels stay in the L1 by themselves (the four-wide kernel gains 11 % from its copy), so: off
     int descend_min_wide = 24;       // the same for the eight-wide kernel (12 / 16 / 24: 228 / 234 / 237 Mpaths/s on the synthetic scene)
     int descend_min = 16;            // lanes that must still be descending for the node loop to go on
     int trace_threads = 512;         // CTA size of the trace kernel (256, 512 or 1024): copies of the BVH's top levels per SM

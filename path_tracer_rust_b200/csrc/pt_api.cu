@@ -527,6 +527,7 @@ extern "C" int ptb_set_option(ptb_ctx *ctx, const char *key, double value) {
     else if (k == "bvh_leaf_max") ctx->bvh_opt.leaf_max = ctx->bvh_opt.leaf_max_small = (int)value;
     else if (k == "bvh_sah_max_prims") ctx->bvh_opt.sah_max_prims = (int)std::max(0.0, std::min(1e9, value));
     else if (k == "bvh_wide") ctx->bvh_opt.wide = (int)value;
+    else if (k == "bvh_wide_sah") ctx->bvh_opt.wide_sah = (int)value;
     else if (k == "bvh_top_levels") ctx->bvh_opt.top_levels = std::max(0, std::min(5, (int)value));
     else if (k == "wf_refill") ctx->wf_opt.refill = (int)value;
     else if (k == "wf_descend_min") ctx->wf_opt.descend_min = ctx->wf_opt.descend_min_wide = (int)value;

@@ -39,7 +39,11 @@ struct Bvh8Box { float lo[3], hi[3]; };
 //   d_bound       bound on |ray origin - anything| + coordinates (the D + coord_max of the padding)
 //   out_nodes     6 x 4 x uint32 per wide node               out_order    wide primitive order: position -> leaf position k
 // Returns the depth of the wide tree (0 = failed: more than 2^28 nodes).
+//   sah_collapse  > 0: the children of every wide node are chosen by the surface-area cost recurrence of Ylitie et al. (section 3.1,
+//                 dynamic programme over the binary tree) with a primitive weighing sah_collapse / 4 node visits; 0: greedily, opening
+//                 the child with the largest surface area
 int bvh8_collapse(int n_prims, const int *left, const int *right, const int *first, const int *last, const Bvh8Box *node_box,
-                  const Bvh8Box *leaf_box, double d_bound, std::vector<uint32_t> &out_nodes, std::vector<int> &out_order);
+                  const Bvh8Box *leaf_box, double d_bound, std::vector<uint32_t> &out_nodes, std::vector<int> &out_order,
+                  int sah_collapse = 2);
 
 }  // namespace ptb

@@ -21,7 +21,7 @@ inline double area(const Bvh8Box &b) {
 }  // namespace
 
 int bvh8_collapse(int n, const int *left, const int *right, const int *first, const int *last, const Bvh8Box *node_box,
-                  const Bvh8Box *leaf_box, double d_bound, std::vector<uint32_t> &nodes, std::vector<int> &order) {
+                  const Bvh8Box *leaf_box, double d_bound, std::vector<uint32_t> &nodes, std::vector<int> &order, int sah_collapse) {
     nodes.clear();
     order.clear();
     if (n <= 0) return 0;
@@ -31,6 +31,79 @@ int bvh8_collapse(int n, const int *left, const int *right, const int *first, co
     auto ref_size = [&](int r) { return ref_last(r) - ref_first(r) + 1; };
     auto ref_box = [&](int r) -> const Bvh8Box & { return r < 0 ? leaf_box[~r] : node_box[r]; };
     auto is_leaf = [&](int r) { return ref_size(r) <= BVH8_LEAF_MAX; };
+
+    // ---- pass 0 (optional): which binary subtrees become the children of a wide node, by the cost recurrence of Ylitie et al. 3.1:
+    //   C(n, 1) = min( leaf cost, A_n c_node + D(n, 8) )          one root: a leaf child, or a wide node whose children are a forest of <= 8
+    //   C(n, i) = min( D(n, i), C(n, i - 1) )   i = 2..7          a forest of at most i roots covering n's primitives, no node at n
+    //   D(n, j) = min over 0 < k < j of C(left, k) + C(right, j - k)
+    // with A the surface area; a leaf child costs A c_prim per primitive (one primitive per leaf child here).
+    constexpr float C_NODE = 1.0f, INF = 3e38f;
+    const float C_PRIM = 0.25f * (float)std::max(1, sah_collapse);  // (sah_collapse doubles as the weight in quarters: 2 = 0.5)
+    struct Dp { float c[8]; uint8_t split[9]; uint8_t internal; };  // c[i], i = 1..7; split[j]: the k of D(n, j), 0 = "use C(n, j-1)"; internal: C(n,1) is a wide node
+    std::vector<Dp> dp;
+    auto cost_of = [&](int r, int i) -> float {  // C(r, i) for a child ref
+        if (r < 0) return (float)area(leaf_box[~r]) * C_PRIM;
+        return dp[r].c[i];
+    };
+    if (sah_collapse && n > 1) {
+        dp.resize((size_t)n - 1);
+        // children before parents: explicit post-order walk
+        std::vector<int> walk;
+        walk.reserve((size_t)n);
+        {
+            std::vector<int> st;
+            st.push_back(0);
+            while (!st.empty()) {
+                const int b = st.back();
+                st.pop_back();
+                walk.push_back(b);
+                if (left[b] >= 0) st.push_back(left[b]);
+                if (right[b] >= 0) st.push_back(right[b]);
+            }
+        }
+        for (size_t w = walk.size(); w-- > 0;) {
+            const int b = walk[w], l = left[b], r = right[b];
+            Dp &d = dp[b];
+            float dist[9];
+            dist[0] = dist[1] = INF;
+            d.split[0] = d.split[1] = 0;
+            for (int j = 2; j <= 8; ++j) {
+                float best = INF;
+                int bk = 1;
+                for (int k = 1; k < j; ++k) {
+                    if (k > 7 || j - k > 7) continue;
+                    const float v = cost_of(l, k) + cost_of(r, j - k);
+                    if (v < best) { best = v; bk = k; }
+                }
+                dist[j] = best;
+                d.split[j] = (uint8_t)bk;
+            }
+            const float a_n = (float)area(node_box[b]);
+            const float c_int = a_n * C_NODE + dist[8];
+            const float c_leaf = is_leaf(b) ? a_n * C_PRIM * (float)ref_size(b) : INF;
+            d.internal = c_int < c_leaf ? 1 : 0;
+            d.c[0] = INF;
+            d.c[1] = std::min(c_int, c_leaf);
+            for (int i = 2; i <= 7; ++i) {
+                if (dist[i] < d.c[i - 1]) d.c[i] = dist[i];
+                else { d.c[i] = d.c[i - 1]; d.split[i] = 0; }  // fewer roots are at least as good
+            }
+        }
+    }
+    // the children of the wide node that stands for binary node `b`, following the recurrence's decisions
+    struct Collect {
+        const int *left, *right;
+        const std::vector<Dp> *dp;
+        int *c;
+        int nc;
+        void run(int m, int budget) {
+            if (m < 0 || budget <= 1) { c[nc++] = m; return; }  // a root of the forest: leaf child or wide node (decided when it is visited)
+            const uint8_t k = (*dp)[m].split[budget];
+            if (k == 0) { run(m, budget - 1); return; }
+            run(left[m], k);
+            run(right[m], budget - k);
+        }
+    };
 
     // ---- pass 1 (sequential, breadth first): children of every wide node, their slots, the numbering of nodes and primitives
     struct Wide {
@@ -70,7 +143,13 @@ int bvh8_collapse(int n, const int *left, const int *right, const int *first, co
                 const Bvh8Box &nb = bin < 0 ? leaf_box[0] : node_box[bin];
                 if (bin < 0) c[nc++] = ~0;  // the whole set is one primitive
                 else if (is_leaf(bin)) c[nc++] = bin;  // (the root itself is small enough to be one leaf child)
-                else {
+                else if (!dp.empty()) {
+                    Collect col{left, right, &dp, c, 0};
+                    const uint8_t k = dp[bin].split[8];
+                    col.run(left[bin], k);
+                    col.run(right[bin], 8 - k);
+                    nc = col.nc;
+                } else {
                     c[nc++] = left[bin];
                     c[nc++] = right[bin];
                     float ar[8];

@@ -680,7 +680,7 @@ cudaError_t bvh_build(const ptb_scene_desc &desc, const std::vector<char> &in_bv
             std::vector<uint32_t> wn;
             std::vector<int> order;
             const int wdepth = bvh8_collapse(n, h_left.data(), h_right.data(), h_first.data(), h_last.data(), nb.data(), lb.data(),
-                                             (double)D + coord_max, wn, order);
+                                             (double)D + coord_max, wn, order, opt.wide_sah);
             if (wdepth > 0 && wdepth + 2 <= BVH_STACK && (int)order.size() == n) {
                 const size_t nw = wn.size() / 24;
                 if (out.cap_nodes8 < nw) {

@@ -34,6 +34,7 @@ struct BvhOptions {
     int sah_max_prims = 16384; // sets up to this size get a binned-SAH topology from the host, larger ones the device LBVH (Karras)
     int wide = -1;            // compressed eight-wide BVH for the wavefront trace kernel (pt_bvh8.h): 1 = build it, 0 = never, -1 = when the
                               // set is too large for the host SAH build (measured: synthetic 1.3 M triangles +7 %, mesh.json 810 triangles -6 %)
+    int wide_sah = 2;         // eight-wide collapse by the surface-area cost recurrence (1) or greedily by largest area (0)
     int top_levels = 5;       // four-wide levels copied for the trace kernel's shared memory (0..5); measured on B200: 0 -> 4 levels +6 %, 5 levels (512-thread CTAs) +11 %
 #ifdef PTB_EXPERIMENTS
     double pad_scale = 1.0;   // scales the conservative box padding; anything below 1 voids the parity guarantee

@@ -137,7 +137,9 @@ int ptb_flatten_loose(const ptb_scene_desc *desc, double quad_min_ratio, float *
  *   "bvh_wide"        compressed eight-wide BVH for the wavefront trace kernel: 1 = always, 0 = never, -1 = for large sets (default)
  *   "bvh_sah_max_prims" sets up to this size get a binned-SAH topology built on the host instead of the device LBVH (default 16384)
  *   "bvh_leaf_max" (1..8, default 2), "bvh_top_levels" (0..5: four-wide levels the trace kernel keeps in shared memory),
- *   "wf_refill", "wf_descend_min", "wf_trace_threads" (256 / 512 / 1024): traversal tuning, see DESIGN.md
+ *   "wf_refill", "wf_descend_min", "wf_trace_threads" (256 / 512 / 1024), "wf_top8_nodes" (eight-wide nodes staged in shared memory,
+ *   default 0), "bvh_wide_sah" (eight-wide collapse by the surface-area cost recurrence, default on; 0 = greedy): traversal tuning,
+ *   see DESIGN.md
  *   "quad_min_ratio"  a two-triangle mesh whose bounding-sphere radius is at least this fraction of the scene diagonal is tested
  *                     without the per-mesh warp vote (default 0.125; 0 = every two-triangle mesh, a huge value = none)
  *   "regen_batch"     lanes that must be waiting for a camera ray before the ray-generation code runs (default 24) */

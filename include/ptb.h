@@ -173,8 +173,8 @@ int ptb_render_progressive(ptb_ctx *ctx, int width, int height, uint64_t spp_beg
 
 /* Same, accumulating into a caller-provided DEVICE sum framebuffer (W*H*3 fp32, += in sample order) on
  * `cuda_stream` (a cudaStream_t; NULL = the default stream).  Asynchronous unless cancel/samples_done is given.  The kernels use
- * per-context state (queues, counters, BVH, scene buffers): before the next call that touches the context on ANOTHER stream --
- * ptb_upload_scene, ptb_render, a ptb_render_device with a different stream -- wait for this one (ptb_device_sync or ptb_get_stats). */
+ * per-context state (queues, counters, BVH, scene buffers); the library orders the next render / upload on this context after this
+ * one with an event, whatever stream it runs on.  The CALLER's buffer (d_sum_rgb) is the caller's to synchronise. */
 int ptb_render_device(ptb_ctx *ctx, int width, int height, uint64_t spp_begin, uint64_t spp_count, uint64_t seed,
                       float *d_sum_rgb, void *cuda_stream, const volatile int32_t *cancel,
                       volatile uint64_t *samples_done);

@@ -68,6 +68,8 @@ struct ptb_ctx {
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_done = nullptr;  // end of the last render on whatever stream it ran: the next user of the context's buffers waits for it
+    bool render_in_flight = false;
     std::string err;
     bool has_scene = false;
     DScene ds{};
@@ -205,6 +207,7 @@ extern "C" void ptb_destroy(ptb_ctx *ctx) {
     wf_release(ctx->wf);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -238,6 +241,7 @@ extern "C" int ptb_create(int device_id, ptb_ctx **out) {
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = ctx->tile_counter.resize(1)) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = ctx->seg_counter.resize(4)) != cudaSuccess) return bail(e, "cudaMalloc");  // segments, BVH nodes, BVH prims, -
     if ((e = ctx->check_word.resize(1)) != cudaSuccess) return bail(e, "cudaMalloc");
@@ -402,6 +406,8 @@ static int upload_scene_one(ptb_ctx *ctx, const ptb_scene_desc *desc) {
     int code = PTB_OK;
     if (const char *why = validate_desc(desc, code)) return fail(ctx, code, std::string("ptb_upload_scene: ") + why);
     CU(ctx, cudaSetDevice(ctx->device));
+    // an asynchronous ptb_render_device on a caller's stream may still be reading the scene buffers this call rewrites
+    if (ctx->render_in_flight) { CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_done, 0)); CU(ctx, cudaEventSynchronize(ctx->ev_done)); ctx->render_in_flight = false; }
     const double t0 = now_ms();
     const size_t nobj = desc->n_objects;
 
@@ -631,6 +637,9 @@ int render_device_impl(ptb_ctx *ctx, int width, int height, uint64_t spp_begin, 
 
     ctx->stats.kernel_launches = 0;
     ctx->stats.samples = 0;
+    // the kernels use per-context state (queues, counters, workspace): order this render after the previous one even when the
+    // caller switched streams in between
+    if (ctx->render_in_flight) CU(ctx, cudaStreamWaitEvent(st, ctx->ev_done, 0));
     CU(ctx, cudaMemsetAsync(ctx->seg_counter.p, 0, 4 * sizeof(unsigned long long), st));
     CU(ctx, cudaEventRecord(ctx->ev0, st));
     const uint64_t npix = static_cast<uint64_t>(width) * static_cast<uint64_t>(height);
@@ -706,6 +715,8 @@ int render_device_impl(ptb_ctx *ctx, int width, int height, uint64_t spp_begin, 
     if (fresh_frame && done == 0)  // nothing was rendered (no samples asked for, or cancelled at once): the frame is black
         CU(ctx, cudaMemsetAsync(d_sum_rgb, 0, npix * 3 * sizeof(float), st));
     CU(ctx, cudaEventRecord(ctx->ev1, st));
+    CU(ctx, cudaEventRecord(ctx->ev_done, st));
+    ctx->render_in_flight = true;
     ctx->stats.samples = done * npix;
     ctx->stats_pending = true;
     ctx->pending_stream = st;

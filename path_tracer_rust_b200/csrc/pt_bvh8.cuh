@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <string.h>
 
+#include "pt_bvh8.h"
+
 #ifdef __CUDACC__
 #define PTB_HD __host__ __device__ __forceinline__
 #else
@@ -76,8 +78,10 @@ PTB_HD uint32_t bvh8_node_hits(const Bvh8Node &n, float ox, float oy, float oz, 
             const float t0z = fmaf(bvh8_byte_as_biased_float<k>(nz, magic), az, bz), t1z = fmaf(bvh8_byte_as_biased_float<k>(fz, magic), az, bz); \
             const float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.0f));                                                     \
             const float tf = fminf(fminf(t1x, t1y), fminf(t1z, tmax));                                                     \
-            /* branch-free: an empty slot has meta 0 and adds nothing; an inner child sets bit 24 + slot for now */       \
-            hits |= (tn <= tf ? (bits4 >> (8 * k)) & 0xffu : 0u) << ((at4 >> (8 * k)) & 0xffu);                            \
+            /* branch-free: an empty slot's box is inverted and never hit; an inner child sets bit 24 + slot for now;   */ \
+            /* with one primitive per leaf child every used slot contributes exactly one bit                            */ \
+            if (BVH8_LEAF_MAX == 1) hits |= (tn <= tf ? 1u : 0u) << ((at4 >> (8 * k)) & 0xffu);                            \
+            else hits |= (tn <= tf ? (bits4 >> (8 * k)) & 0xffu : 0u) << ((at4 >> (8 * k)) & 0xffu);                       \
         }
         PTB_BVH8_CHILD(0) PTB_BVH8_CHILD(1) PTB_BVH8_CHILD(2) PTB_BVH8_CHILD(3)
 #undef PTB_BVH8_CHILD

@@ -266,7 +266,10 @@ int bvh8_collapse(int n, const int *left, const int *right, const int *first, co
             }
             uint32_t imask = 0;
             uint8_t meta[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[6][8];
-            std::memset(q, 0, sizeof q);
+            // an empty slot gets an inverted box (lower planes at 255, upper planes at 0): no ray can hit it, whatever its direction,
+            // so the node test needs no "is this slot used" decision
+            for (int sl = 0; sl < 8; ++sl)
+                for (int a = 0; a < 3; ++a) { q[a][sl] = 255; q[3 + a][sl] = 0; }
             int prim_off = 0;
             for (int sl = 0; sl < 8; ++sl) {
                 const int r = W.child[sl];

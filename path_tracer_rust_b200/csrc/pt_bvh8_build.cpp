@@ -47,22 +47,11 @@ int bvh8_collapse(int n, const int *left, const int *right, const int *first, co
     };
     if (sah_collapse && n > 1) {
         dp.resize((size_t)n - 1);
-        // children before parents: explicit post-order walk
-        std::vector<int> walk;
-        walk.reserve((size_t)n);
-        {
-            std::vector<int> st;
-            st.push_back(0);
-            while (!st.empty()) {
-                const int b = st.back();
-                st.pop_back();
-                walk.push_back(b);
-                if (left[b] >= 0) st.push_back(left[b]);
-                if (right[b] >= 0) st.push_back(right[b]);
-            }
-        }
-        for (size_t w = walk.size(); w-- > 0;) {
-            const int b = walk[w], l = left[b], r = right[b];
+        // children before parents.  The tree is cut a few levels below the root: the subtrees below the cut are independent and
+        // are solved by one thread each (reverse pre-order inside a subtree visits children before parents), the few nodes above
+        // the cut afterwards.
+        auto solve = [&](int b) {
+            const int l = left[b], r = right[b];
             Dp &d = dp[b];
             float dist[9];
             dist[0] = dist[1] = INF;
@@ -88,7 +77,43 @@ int bvh8_collapse(int n, const int *left, const int *right, const int *first, co
                 if (dist[i] < d.c[i - 1]) d.c[i] = dist[i];
                 else { d.c[i] = d.c[i - 1]; d.split[i] = 0; }  // fewer roots are at least as good
             }
+        };
+        auto solve_subtree = [&](int root) {
+            std::vector<int> walk, st;
+            st.push_back(root);
+            while (!st.empty()) {
+                const int b = st.back();
+                st.pop_back();
+                walk.push_back(b);
+                if (left[b] >= 0) st.push_back(left[b]);
+                if (right[b] >= 0) st.push_back(right[b]);
+            }
+            for (size_t w = walk.size(); w-- > 0;) solve(walk[w]);
+        };
+        std::vector<int> top, cut;  // nodes above the cut (pre-order), roots of the subtrees below it
+        {
+            std::vector<std::pair<int, int>> st;
+            st.push_back({0, 0});
+            while (!st.empty()) {
+                const auto [b, depth] = st.back();
+                st.pop_back();
+                if (depth >= 6) { cut.push_back(b); continue; }
+                top.push_back(b);
+                if (left[b] >= 0) st.push_back({left[b], depth + 1});
+                if (right[b] >= 0) st.push_back({right[b], depth + 1});
+            }
         }
+        {
+            const unsigned hw_dp = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+            if (cut.size() < 2 || hw_dp == 1 || n < 20000) for (int c : cut) solve_subtree(c);
+            else {
+                std::vector<std::thread> th;
+                for (unsigned t = 0; t < hw_dp; ++t)
+                    th.emplace_back([&, t] { for (size_t i = t; i < cut.size(); i += hw_dp) solve_subtree(cut[i]); });
+                for (auto &x : th) x.join();
+            }
+        }
+        for (size_t w = top.size(); w-- > 0;) solve(top[w]);
     }
     // the children of the wide node that stands for binary node `b`, following the recurrence's decisions
     struct Collect {

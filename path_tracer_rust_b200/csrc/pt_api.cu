@@ -535,9 +535,9 @@ extern "C" int ptb_set_option(ptb_ctx *ctx, const char *key, double value) {
     else if (k == "bvh_wide") ctx->bvh_opt.wide = (int)value;
     else if (k == "bvh_wide_sah") ctx->bvh_opt.wide_sah = (int)value;
     else if (k == "bvh_top_levels") ctx->bvh_opt.top_levels = std::max(0, std::min(5, (int)value));
-    else if (k == "wf_refill") ctx->wf_opt.refill = (int)value;
+    else if (k == "wf_refill") ctx->wf_opt.refill = ctx->wf_opt.refill_wide = (int)value;
     else if (k == "wf_descend_min") ctx->wf_opt.descend_min = ctx->wf_opt.descend_min_wide = (int)value;
-    else if (k == "wf_trace_threads") ctx->wf_opt.trace_threads = (int)value;
+    else if (k == "wf_trace_threads") ctx->wf_opt.trace_threads = ctx->wf_opt.trace_threads_wide = (int)value;
     else if (k == "wf_top8_nodes") ctx->wf_opt.top8_nodes = (int)value;
     else if (k == "quad_min_ratio") ctx->quad_min_ratio = value;
     else if (k == "regen_batch") ctx->regen_batch = std::max(1, std::min(32, (int)value));

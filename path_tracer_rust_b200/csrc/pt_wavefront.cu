@@ -574,8 +574,9 @@ cudaError_t wavefront_render(const DScene &scene, const RenderArgs &a, WfWorkspa
     TraceLaunch tl;
     if (has_bvh) {
         // the CTA size trades copies of the top levels per SM against scheduling granularity (opt.trace_threads: 256, 512 or 1024)
-        if (opt.trace_threads >= 1024) e = trace_config<1024>(sc, sm_count, tl);
-        else if (opt.trace_threads >= 512) e = trace_config<512>(sc, sm_count, tl);
+        const int threads = sc.n_bvh8_nodes > 0 ? opt.trace_threads_wide : opt.trace_threads;
+        if (threads >= 1024) e = trace_config<1024>(sc, sm_count, tl);
+        else if (threads >= 512) e = trace_config<512>(sc, sm_count, tl);
         else e = trace_config<256>(sc, sm_count, tl);
         if (e != cudaSuccess) return e;
     }
@@ -595,8 +596,9 @@ cudaError_t wavefront_render(const DScene &scene, const RenderArgs &a, WfWorkspa
             const WfQueue &cur = w.q[b & 1], &nxt = w.q[(b + 1) & 1];
             int *ctr = w.counters + WF_CTR_STRIDE * b;
             if (has_bvh) {
-                tl.kern<<<tl.blocks, tl.threads, tl.smem, st>>>(sc, cur, ctr, ctr + 2, a.segment_counter, opt.refill,
-                                                                sc.n_bvh8_nodes > 0 ? opt.descend_min_wide : opt.descend_min);
+                const bool wide = sc.n_bvh8_nodes > 0;
+                tl.kern<<<tl.blocks, tl.threads, tl.smem, st>>>(sc, cur, ctr, ctr + 2, a.segment_counter, wide ? opt.refill_wide : opt.refill,
+                                                                wide ? opt.descend_min_wide : opt.descend_min);
                 (*launches)++;
             }
             k_wf_shade<<<wide, 256, smem, st>>>(sc, cur, ctr, nxt, ctr + WF_CTR_STRIDE, w.slots, w.branch_mask, (unsigned)n_paths, npix, s0,

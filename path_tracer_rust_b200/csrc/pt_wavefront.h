@@ -41,6 +41,8 @@ struct WfOptions {
     int top8_nodes = 0;              // nodes of the eight-wide BVH (breadth first) staged in shared memory, <= BVH8_TOP_MAX.  Measured on
                                      // B200: 0 / 73 / 256 / 512 nodes = 236.9 / 235.5 / 235.6 / 237.3 Mpaths/s -- the 96-byte nodes of the top
                                      // levels stay in the L1 by themselves (the four-wide kernel gains 11 % from its copy), so: off
+    int refill_wide = 4, trace_threads_wide = 1024;  // the eight-wide kernel's refill threshold and CTA size (measured: 8 / 512 -> 246.5,
+                                     // 4 / 512 -> 251.9, 8 / 1024 -> 249.6, 4 / 1024 -> 255.6 Mpaths/s on the synthetic scene)
     int descend_min_wide = 24;       // the same for the eight-wide kernel (12 / 16 / 24: 228 / 234 / 237 Mpaths/s on the synthetic scene)
     int descend_min = 16;            // lanes that must still be descending for the node loop to go on
     int trace_threads = 512;         // CTA size of the trace kernel (256, 512 or 1024): copies of the BVH's top levels per SM
